@@ -1,0 +1,403 @@
+// oracle/ref_driver.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Builds the *unmodified* reference planner (vdBerg93/cl-rrt, rrt/src/*.cpp, compiled
+// from where it lies under /root/reference by oracle/build_ref.sh) into a shared
+// library with a flat C interface, so that tests/golden/make_golden.py and the
+// bench's cpu_baseline leg can run the reference's own expandTree / Simulation /
+// sortNodes* / getOBBdist on chosen inputs.  No reference source is copied into this
+// repository: the files are #include'd by name and resolved through -I at build time.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// legs may load the resulting oracle/_ref/*.so.
+//
+// The reference is one translation unit (rrt/src/rrt_node.cpp:26 -> rrt/src/include.cpp);
+// this file plays the role of rrt_node.cpp: it defines the same file-scope globals
+// (rrt/src/rrt_node.cpp:2-24) and then includes the planner sources in the order of
+// rrt/src/include.cpp:38-44, with ONE difference: the shipped collision stub
+// (rrt/src/collisioncheck.cpp:6-8, "return 100") is replaced by a run-time switch
+// between that stub and the uncompiled-upstream OBB/SAT code of
+// rrt/src/old_collisioncheck.cpp:24-51.
+//
+// Variant REF_DEFINED (second .so) is compiled from sed-patched temporaries of three
+// reference files (see build_ref.sh) that clamp the reference's out-of-bounds reads
+// (SURVEY.md §8c "UB-tainted rollouts"); the patched copies live in a temp dir only.
+
+#include <ros/ros.h>
+#include <iostream>
+#include <vector>
+#include <array>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <ctime>
+#include <chrono>
+#include <geometry_msgs/Point.h>
+#include <visualization_msgs/Marker.h>
+#include <visualization_msgs/MarkerArray.h>
+#include <std_msgs/Float64MultiArray.h>
+#include <std_msgs/MultiArrayDimension.h>
+#include <vision_msgs/Detection2DArray.h>
+#include "car_msgs/getobstacles.h"
+#include "car_msgs/MotionRequest.h"
+#include "car_msgs/MotionResponse.h"
+#include "car_msgs/State.h"
+#include "car_msgs/Trajectory.h"
+#include "car_msgs/MotionPlan.h"
+#include "car_msgs/Obstacle2D.h"
+#include "car_msgs/resetplanner.h"
+
+// ---- globals of rrt/src/rrt_node.cpp:2-24 (same names: the planner sources use them) ----
+bool draw_tree = 0;  // upstream 1; only gates rviz marker building in extractBestPath
+bool draw_obs = 0;
+bool draw_final_path = 0;
+bool debug_mode = 0;
+bool debug_reference = 0;
+bool debug_velocity = 0;
+bool draw_states = 0;
+bool debug_sim = 0;
+bool commit_path = false;
+bool obs_use_pred = true;
+double Tcommit{0.25};
+double sim_dt;
+double ctrl_tla, ctrl_dla, ctrl_mindla, ctrl_dlavmin, ctrl_Kp, ctrl_Ki;
+double ref_res, ref_int, ref_mindist, vmax, vgoal;
+double ay_road_max;
+int fail_iterlimit{0};
+int fail_collision{0};
+int fail_acclimit{0};
+int sim_count{0};
+
+#include "rrt/functions.h"
+#include "rrt/vehicle.h"
+#include "rrt/rrtplanner.h"
+#include "rrt/simulation.h"
+#include "rrt/collision.h"
+#include "rrt/controller.h"
+#include "rrt/datatypes.h"
+#include "rrt/motionplanner.h"
+#include "car_msgs/Reference.h"
+
+// ---- collision hook (the only glue between the live sources and old_collisioncheck.cpp) ----
+double checkObsDistance(const vector<double>& states, const vector<car_msgs::Obstacle2D>& det,
+                        const vector<double>& carState);
+static const vector<car_msgs::Obstacle2D>* g_det = nullptr;  // null => shipped stub behaviour
+static vector<double> g_carState(6, 0.0);
+static long g_sat_calls = 0;
+#include "old_collisioncheck.cpp"
+double checkObsDistance(const vector<double>& x) {
+  // rrt/src/simulation.cpp:83 calls this 1-argument form after every sim step.
+  if (g_det == nullptr || x.size() < 7) return 100;  // == rrt/src/collisioncheck.cpp:6-8
+  g_sat_calls += (long)g_det->size();
+  return checkObsDistance(x, *g_det, g_carState);  // rrt/src/old_collisioncheck.cpp:24-51
+}
+
+#include "reference.cpp"
+#include "rrtplanner.cpp"
+#include "controller.cpp"
+#include "simulation.cpp"
+#include "motionplanner.cpp"
+
+// ------------------------------------------------------------------------------------------
+namespace {
+Vehicle g_veh;
+MyRRT* g_rrt = nullptr;
+vector<car_msgs::Obstacle2D> g_obstacles;
+vector<double> g_goal{50, 0, 0, 0};
+
+void set_launch_params() {
+  // rrt/launch/parameters.launch:3-20
+  ros::param::set("ctrl/tla", 1.4);
+  ros::param::set("ctrl/mindla", 3.2);
+  ros::param::set("ctrl/dlavmin", 3);
+  ros::param::set("ctrl/refint", 0.02);
+  ros::param::set("ctrl/refmindist", 0.2);
+  ros::param::set("ctrl/sampleTime", 0.04);
+  ros::param::set("ctrl/Kp", 8);
+  ros::param::set("ctrl/Ki", 0.05);
+  ros::param::set("motionplanner/weight_distance", 10);
+  ros::param::set("motionplanner/weight_curvature", 5);
+  ros::param::set("motionplanner/weight_obstacle_gain", 0);
+  ros::param::set("motionplanner/weight_obstacle_slope", 4);
+  ros::param::set("motionplanner/weight_lanedeviation", 1);
+}
+void read_params() {
+  // rrt/src/rrt_node.cpp:28-38 (updateParameters)
+  ros::param::get("ctrl/tla", ctrl_tla);
+  ros::param::get("ctrl/mindla", ctrl_mindla);
+  ros::param::get("ctrl/dlavmin", ctrl_dlavmin);
+  ros::param::get("ctrl/refint", ref_int);
+  ros::param::get("ctrl/refmindist", ref_mindist);
+  ros::param::get("ctrl/sampleTime", sim_dt);
+  ros::param::get("ctrl/Kp", ctrl_Kp);
+  ros::param::get("ctrl/Ki", ctrl_Ki);
+}
+enum { NODE_STRIDE = 20, OUT_STRIDE = 24 };
+
+void fill_out(double* o, const Simulation& sim, const MyReference& ref, int c0, int a0, int i0) {
+  const vector<double>& xf = sim.stateArray.back();
+  for (int k = 0; k < 10; k++) o[k] = xf[k];
+  o[10] = sim.costE;
+  o[11] = sim.costS;
+  o[12] = sim.endReached;
+  o[13] = sim.goalReached;
+  o[14] = (double)sim.stateArray.size() - 1;  // executed sim steps
+  int code = 0;
+  if (fail_collision != c0) code = 1;
+  else if (fail_acclimit != a0) code = 2;
+  else if (fail_iterlimit != i0) code = 3;
+  o[15] = code;
+  const int N = (int)ref.x.size();
+  o[16] = N;
+  o[17] = ref.x.back();
+  o[18] = ref.y.back();
+  o[19] = ref.v.empty() ? 0.0 : ref.v.back();
+  // taint: any step used a waypoint index >= N-2 (then ref.v[IDwp+2] / ref.x[IDwp+1] were read
+  // past the end in the unmodified reference).  x[7] logs the IDwp used.
+  int tainted = 0;
+  double trace = 0;
+  for (size_t i = 1; i < sim.stateArray.size(); i++) {
+    const int id = (int)sim.stateArray[i][7];
+    if (id >= N - 2) tainted = 1;
+    trace += (double)i * (double)id;
+  }
+  o[20] = tainted;
+  o[21] = trace;  // checksum of the per-step waypoint-index trace
+  o[22] = sim.stateArray[0][7];  // waypoint index chosen by the Controller ctor
+  o[23] = 0;
+}
+}  // namespace
+
+extern "C" {
+
+int ref_is_defined_variant() {
+#ifdef REF_DEFINED
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+// Launch-file parameters + Prius vehicle (rrt/src/motionplanner.cpp:13).
+void ref_init(void) {
+  set_launch_params();
+  read_params();
+  g_veh.setPrius();
+  ay_road_max = 0;
+  vmax = 5;
+  vgoal = 0;
+}
+void ref_set_weights(const double* w5) {
+  ros::param::set("motionplanner/weight_distance", w5[0]);
+  ros::param::set("motionplanner/weight_curvature", w5[1]);
+  ros::param::set("motionplanner/weight_obstacle_gain", w5[2]);
+  ros::param::set("motionplanner/weight_obstacle_slope", w5[3]);
+  ros::param::set("motionplanner/weight_lanedeviation", w5[4]);
+}
+void ref_get_vehicle(double* v14) {
+  const double a[14] = {g_veh.dmax, g_veh.ddmax, g_veh.Td, g_veh.Ta, g_veh.amin, g_veh.amax, g_veh.L,
+                        g_veh.w, g_veh.Lrear, g_veh.Lfront, g_veh.b, g_veh.Vch, g_veh.rho, g_veh.Kus};
+  memcpy(v14, a, sizeof a);
+}
+void ref_srand(unsigned seed) { srand(seed); }
+
+// obstacles: n x {cx, cy, theta, size_x, size_y, vx, vy} (car_msgs/msg/Obstacle2D.msg).
+// n == 0 selects the shipped stub (rrt/src/collisioncheck.cpp:6-8).
+void ref_set_obstacles(const double* o7, int n) {
+  g_obstacles.clear();
+  for (int i = 0; i < n; i++) {
+    car_msgs::Obstacle2D o;
+    o.obb.center.x = o7[7 * i + 0];
+    o.obb.center.y = o7[7 * i + 1];
+    o.obb.center.theta = o7[7 * i + 2];
+    o.obb.size_x = o7[7 * i + 3];
+    o.obb.size_y = o7[7 * i + 4];
+    o.vel.linear.x = o7[7 * i + 5];
+    o.vel.linear.y = o7[7 * i + 6];
+    g_obstacles.push_back(o);
+  }
+  g_det = n > 0 ? &g_obstacles : nullptr;
+  if (g_rrt) g_rrt->det = g_obstacles;
+}
+
+// Start of MotionPlanner::planMotion (rrt/src/motionplanner.cpp:9-32) with commit_path=false:
+// counters reset, lookahead / reference resolution from the car speed, new MyRRT, root node.
+void ref_tree_init(const double* car_state6, const double* goal4, double vmax_) {
+  fail_acclimit = 0; fail_collision = 0; fail_iterlimit = 0; sim_count = 0;
+  vector<double> worldState(car_state6, car_state6 + 6);
+  vector<double> carPose = transformStateToLocal(worldState);
+  updateLookahead(carPose[4]);
+  updateReferenceResolution(carPose[4]);
+  g_goal.assign(goal4, goal4 + 4);
+  vmax = vmax_;
+  vgoal = goal4[3];
+  delete g_rrt;
+  vector<double> laneShifts{0}, Cxy;
+  g_rrt = new MyRRT(g_goal, laneShifts, Cxy, false);
+  g_rrt->det = g_obstacles;
+  g_rrt->carState = carPose;
+  g_carState = carPose;
+  vector<Node> none;
+  initializeTree(*g_rrt, g_veh, none, carPose);
+}
+double ref_get_ref_res(void) { return ref_res; }
+
+// iters calls of expandTree (rrt/src/rrtplanner.cpp:123-174); returns the tree size.
+int ref_expand(int iters) {
+  vector<double> Cxy;
+  for (int i = 0; i < iters; i++) expandTree(g_veh, *g_rrt, nullptr, g_obstacles, Cxy);
+  return (int)g_rrt->tree.size();
+}
+// The 200 ms loop of rrt/src/motionplanner.cpp:39-43 with the reference's own Timer (CPU time).
+int ref_expand_timed(double budget_ms, int* iters_out) {
+  vector<double> Cxy;
+  Timer timer(budget_ms);
+  int iter = 0;
+  for (; timer.Get(); iter++) expandTree(g_veh, *g_rrt, nullptr, g_obstacles, Cxy);
+  if (iters_out) *iters_out = iter;
+  return (int)g_rrt->tree.size();
+}
+int ref_tree_size(void) { return g_rrt ? (int)g_rrt->tree.size() : 0; }
+void ref_counters(int* c4) {
+  c4[0] = fail_collision; c4[1] = fail_acclimit; c4[2] = fail_iterlimit; c4[3] = sim_count;
+}
+long ref_sat_calls(void) { return g_sat_calls; }
+
+// node record: state[10], ref front x,y, ref back x,y, ref.v.back(), costE, costS, parent, goal, nref
+void ref_tree_export(double* out, int cap) {
+  const int n = std::min<int>(cap, (int)g_rrt->tree.size());
+  for (int i = 0; i < n; i++) {
+    const Node& nd = g_rrt->tree[i];
+    double* o = out + (size_t)NODE_STRIDE * i;
+    for (int k = 0; k < 10; k++) o[k] = nd.state[k];
+    o[10] = nd.ref.x.front(); o[11] = nd.ref.y.front();
+    o[12] = nd.ref.x.back();  o[13] = nd.ref.y.back();
+    o[14] = nd.ref.v.back();
+    o[15] = nd.costE; o[16] = nd.costS;
+    o[17] = nd.parentID; o[18] = nd.goalReached; o[19] = (double)nd.ref.x.size();
+  }
+}
+// Replace the tree by records in the export format.  Only the fields the batched primitives read are
+// rebuilt (state, ref front/back, ref.v.back(), costs, parent, goal flag): the reference paths become
+// 2-point stubs, which is all getReference / getGoalReference / feasibleNode / dubinsDistance look at.
+void ref_tree_import(const double* in, int n) {
+  g_rrt->tree.clear();
+  for (int i = 0; i < n; i++) {
+    const double* o = in + (size_t)NODE_STRIDE * i;
+    vector<double> st(o, o + 10);
+    MyReference r;
+    r.x = {o[10], o[12]}; r.y = {o[11], o[13]}; r.v = {o[14], o[14]}; r.dir = 1;
+    vector<state_type> T{st};
+    Node nd(st, (int)o[17], r, T, o[15], o[16], o[18] != 0);
+    g_rrt->tree.push_back(nd);
+  }
+}
+
+// The rollout of rrt/src/rrtplanner.cpp:151-152 (gb=0) or :165-166 (gb=1) for M (parent, sample) pairs.
+// out: M x 24 doubles, see fill_out().  Returns elapsed seconds (steady_clock).
+double ref_rollout_batch(const int* parent, const double* sample_xy, const unsigned char* gb, int M,
+                         double* out) {
+  auto t0 = std::chrono::steady_clock::now();
+  for (int j = 0; j < M; j++) {
+    const int c0 = fail_collision, a0 = fail_acclimit, i0 = fail_iterlimit;
+    const Node& p = g_rrt->tree[parent[j]];
+    if (gb && gb[j]) {
+      MyReference ref = getGoalReference(g_veh, p, g_rrt->goalPose);
+      Simulation sim(*g_rrt, p.state, ref, g_veh, true, true, p.ref.v.back());
+      fill_out(out + (size_t)OUT_STRIDE * j, sim, ref, c0, a0, i0);
+    } else {
+      geometry_msgs::Point s; s.x = sample_xy[2 * j]; s.y = sample_xy[2 * j + 1];
+      MyReference ref = getReference(s, p, 1);
+      Simulation sim(*g_rrt, p.state, ref, g_veh, false, true, p.ref.v.back());
+      fill_out(out + (size_t)OUT_STRIDE * j, sim, ref, c0, a0, i0);
+    }
+  }
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+// Full trajectory of one rollout: traj = up to cap x 10 doubles (stateArray); returns its length.
+int ref_rollout_traj(int parent, const double* sample_xy, int gb, double* traj, int cap, double* refv, int vcap) {
+  const Node& p = g_rrt->tree[parent];
+  MyReference ref;
+  if (gb) ref = getGoalReference(g_veh, p, g_rrt->goalPose);
+  else { geometry_msgs::Point s; s.x = sample_xy[0]; s.y = sample_xy[1]; ref = getReference(s, p, 1); }
+  Simulation sim(*g_rrt, p.state, ref, g_veh, gb != 0, true, p.ref.v.back());
+  const int n = std::min<int>(cap, (int)sim.stateArray.size());
+  for (int i = 0; i < n; i++) for (int k = 0; k < 10; k++) traj[10 * i + k] = sim.stateArray[i][k];
+  if (refv) for (int i = 0; i < std::min<int>(vcap, (int)ref.v.size()); i++) refv[i] = ref.v[i];
+  return (int)sim.stateArray.size();
+}
+
+// sortNodesExplore (heuristic 0) / sortNodesOptimize (1), rrt/src/rrtplanner.cpp:227-268.
+// cand: K x 10 (padded with -1), key: K x 10 float keys of the chosen nodes, count: K.
+double ref_nearest_batch(const double* sample_xy, const unsigned char* heuristic, int K, int* cand,
+                         float* key, int* count) {
+  auto t0 = std::chrono::steady_clock::now();
+  for (int j = 0; j < K; j++) {
+    geometry_msgs::Point s; s.x = sample_xy[2 * j]; s.y = sample_xy[2 * j + 1];
+    vector<int> v = heuristic[j] ? sortNodesOptimize(*g_rrt, s) : sortNodesExplore(*g_rrt, s);
+    count[j] = (int)v.size();
+    for (int r = 0; r < 10; r++) {
+      const bool ok = r < (int)v.size();
+      cand[10 * j + r] = ok ? v[r] : -1;
+      float k = 0;
+      if (ok) {
+        k = dubinsDistance(s, g_rrt->tree[v[r]], g_rrt->direction);
+        if (heuristic[j]) k = g_rrt->tree[v[r]].costE + k;
+      }
+      key[10 * j + r] = k;
+    }
+  }
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+// All keys of one sample (for near-tie audits): key[n_nodes], feasible[n_nodes].
+void ref_keys(const double* sample_xy, int heuristic, float* key, unsigned char* feas) {
+  geometry_msgs::Point s; s.x = sample_xy[0]; s.y = sample_xy[1];
+  for (size_t i = 0; i < g_rrt->tree.size(); i++) {
+    float k = dubinsDistance(s, g_rrt->tree[i], g_rrt->direction);
+    if (heuristic) k = g_rrt->tree[i].costE + k;
+    key[i] = k;
+    feas[i] = feasibleNode(*g_rrt, g_rrt->tree[i], s);
+  }
+}
+float ref_dubins(double sx, double sy, double nx, double ny, double nth, int dir) {
+  geometry_msgs::Point s; s.x = sx; s.y = sy;
+  Node n; n.state = {nx, ny, nth, 0, 0, 0, 0, 0, 0, 0};
+  return dubinsDistance(s, n, dir);
+}
+// getOBBdist(OBB a, OBB b), rrt/src/old_collisioncheck.cpp:98-148; each box = {x, y, w, h, o}.
+double ref_obb_dist(const double* a5, const double* b5) {
+  OBB a(Vector2D(a5[0], a5[1]), a5[2], a5[3], a5[4]);
+  OBB b(Vector2D(b5[0], b5[1]), b5[2], b5[3], b5[4]);
+  return getOBBdist(a, b);
+}
+// checkObsDistance(states, det, carState), rrt/src/old_collisioncheck.cpp:24-51, on one 10-state.
+double ref_obs_distance(const double* x10) {
+  vector<double> x(x10, x10 + 10);
+  return checkObsDistance(x, g_obstacles, g_carState);
+}
+// sampleAroundVehicle + the heuristic draw, in the order of rrt/src/rrtplanner.cpp:133-143.
+void ref_draw_samples(int K, double* sample_xy, unsigned char* heuristic, double* r_out) {
+  for (int j = 0; j < K; j++) {
+    geometry_msgs::Point s = sampleAroundVehicle(g_goal);
+    double r = static_cast<double>(rand()) / (static_cast<double>(RAND_MAX / (1)));
+    sample_xy[2 * j] = s.x; sample_xy[2 * j + 1] = s.y;
+    heuristic[j] = !(r <= 0.7);
+    if (r_out) r_out[j] = r;
+  }
+}
+int ref_feasible_goal_bias(void) { return feasibleGoalBias(*g_rrt); }
+// extractBestPath (rrt/src/rrtplanner.cpp:318-368): node ids root..leaf of the cheapest goal-reaching branch.
+int ref_best_path(int* ids, int cap) {
+  vector<Node> best = extractBestPath(g_rrt->tree, nullptr);
+  // recover ids by walking parents from the cheapest goal node (same rule as :347-358)
+  int bestid = -1; float bestc = 0;
+  for (size_t i = 0; i < g_rrt->tree.size(); i++)
+    if (g_rrt->tree[i].goalReached && (bestid < 0 || (double)g_rrt->tree[i].costS < (double)bestc)) {
+      bestid = (int)i; bestc = g_rrt->tree[i].costS;
+    }
+  vector<int> chain;
+  for (int id = bestid; id != -1; id = g_rrt->tree[id].parentID) chain.insert(chain.begin(), id);
+  const int n = std::min<int>(cap, (int)chain.size());
+  for (int i = 0; i < n; i++) ids[i] = chain[i];
+  return (int)best.size();
+}
+}  // extern "C"
