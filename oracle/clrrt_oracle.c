@@ -452,7 +452,105 @@ static int pair_cmp(const void* a, const void* b) {
   const orc_pair *p = a, *q = b;
   if (p->key < q->key) return -1;
   if (q->key < p->key) return 1;
-  return (p->id > q->id) - (p->id < q->id); /* ties: lower node id first (std::sort is unstable upstream) */
+  return (p->id > q->id) - (p->id < q->id); /* ties: lower node id first */
+}
+/* The reference sorts with std::sort and a key-only comparator (rrtplanner.cpp:234, :256).  std::sort is
+ * unstable, and the reference's trees hold many nodes with identical poses (one-step rollouts from the root),
+ * hence identical keys, so WHICH of several tied parents is tried first is decided by the standard library's
+ * algorithm, not by the reference's source.  Two tie rules are therefore provided:
+ *   tie_mode 0 (default): ties broken by lower node id — the rule the GPU product implements and documents;
+ *   tie_mode 1: a restatement of libstdc++'s std::sort (GCC 13 bits/stl_algo.h: introsort with median-of-3
+ *               pivot, 16-element threshold, final insertion sort, heapsort fallback), which reproduces the
+ *               tie order of the reference binary built in this container; used to pin the oracle against
+ *               whole-tree growth of the reference for arbitrary seeds (tests/test_oracle_vs_reference.py). */
+static int tie_mode = 0;
+#define LESS(a, b) ((a).key < (b).key)
+static void sl_swap(orc_pair* a, orc_pair* b) { orc_pair t = *a; *a = *b; *b = t; }
+static void sl_unguarded_linear_insert(orc_pair* last) {
+  orc_pair val = *last;
+  orc_pair* next = last - 1;
+  while (LESS(val, *next)) { *last = *next; last = next; --next; }
+  *last = val;
+}
+static void sl_insertion_sort(orc_pair* first, orc_pair* last) {
+  if (first == last) return;
+  for (orc_pair* i = first + 1; i != last; ++i) {
+    if (LESS(*i, *first)) {
+      orc_pair val = *i;
+      memmove(first + 1, first, (size_t)(i - first) * sizeof(orc_pair));
+      *first = val;
+    } else sl_unguarded_linear_insert(i);
+  }
+}
+static void sl_push_heap(orc_pair* first, long hole, long top, orc_pair value) {
+  long parent = (hole - 1) / 2;
+  while (hole > top && LESS(first[parent], value)) { first[hole] = first[parent]; hole = parent; parent = (hole - 1) / 2; }
+  first[hole] = value;
+}
+static void sl_adjust_heap(orc_pair* first, long hole, long len, orc_pair value) {
+  const long top = hole;
+  long second = hole;
+  while (second < (len - 1) / 2) {
+    second = 2 * (second + 1);
+    if (LESS(first[second], first[second - 1])) second--;
+    first[hole] = first[second];
+    hole = second;
+  }
+  if ((len & 1) == 0 && second == (len - 2) / 2) {
+    second = 2 * (second + 1);
+    first[hole] = first[second - 1];
+    hole = second - 1;
+  }
+  sl_push_heap(first, hole, top, value);
+}
+static void sl_heapsort(orc_pair* first, orc_pair* last) { /* __partial_sort(first,last,last) */
+  long len = last - first;
+  if (len >= 2)
+    for (long parent = (len - 2) / 2;; parent--) {
+      sl_adjust_heap(first, parent, len, first[parent]);
+      if (parent == 0) break;
+    }
+  while (last - first > 1) {
+    --last;
+    orc_pair value = *last;
+    *last = *first;
+    sl_adjust_heap(first, 0, last - first, value);
+  }
+}
+static void sl_introsort_loop(orc_pair* first, orc_pair* last, long depth) {
+  while (last - first > 16) {
+    if (depth == 0) { sl_heapsort(first, last); return; }
+    --depth;
+    orc_pair *mid = first + (last - first) / 2, *a = first + 1, *b = mid, *c = last - 1;
+    if (LESS(*a, *b)) { /* __move_median_to_first */
+      if (LESS(*b, *c)) sl_swap(first, b);
+      else if (LESS(*a, *c)) sl_swap(first, c);
+      else sl_swap(first, a);
+    } else if (LESS(*a, *c)) sl_swap(first, a);
+    else if (LESS(*b, *c)) sl_swap(first, c);
+    else sl_swap(first, b);
+    orc_pair *lo = first + 1, *hi = last; /* __unguarded_partition(first+1, last, first) */
+    for (;;) {
+      while (LESS(*lo, *first)) ++lo;
+      --hi;
+      while (LESS(*first, *hi)) --hi;
+      if (!(lo < hi)) break;
+      sl_swap(lo, hi);
+      ++lo;
+    }
+    sl_introsort_loop(lo, last, depth);
+    last = lo;
+  }
+}
+static void libstdcxx_sort(orc_pair* first, long n) {
+  if (n == 0) return;
+  long lg = 0;
+  for (long m = n; m > 1; m >>= 1) lg++;
+  sl_introsort_loop(first, first + n, 2 * lg);
+  if (n > 16) {
+    sl_insertion_sort(first, first + 16);
+    for (orc_pair* i = first + 16; i != first + n; ++i) sl_unguarded_linear_insert(i);
+  } else sl_insertion_sort(first, first + n);
 }
 /* sortNodesExplore :227-247 (heuristic 0) / sortNodesOptimize :250-268 (heuristic 1) */
 static int sortNodes(double sx, double sy, int heuristic, int* out, float* keyout) {
@@ -462,7 +560,8 @@ static int sortNodes(double sx, double sy, int heuristic, int* out, float* keyou
     float k = dubinsDistance(sx, sy, tree[i].state, 1);
     d[i].key = heuristic ? tree[i].costE + k : k;
   }
-  qsort(d, (size_t)n_tree, sizeof(orc_pair), pair_cmp);
+  if (tie_mode == 1) libstdcxx_sort(d, n_tree);
+  else qsort(d, (size_t)n_tree, sizeof(orc_pair), pair_cmp);
   int n = 0;
   for (int i = 0; i < n_tree; i++) {
     if (feasibleNode(&tree[d[i].id], sx, sy)) {
@@ -589,6 +688,7 @@ void orc_init(void) {
   veh.Kus = (m / veh.L) * (lr / Cf - lf / Cr);
   veh.Vch = 20;
 }
+void orc_set_tie_mode(int m) { tie_mode = m; }
 void orc_set_weights(const double* w5) { memcpy(Wcost, w5, sizeof Wcost); }
 void orc_get_vehicle(double* v14) { memcpy(v14, &veh, sizeof veh); }
 void orc_srand(unsigned seed) { srand(seed); }

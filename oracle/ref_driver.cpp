@@ -179,6 +179,10 @@ int ref_is_defined_variant() {
 
 // Launch-file parameters + Prius vehicle (rrt/src/motionplanner.cpp:13).
 void ref_init(void) {
+  // The planner prints through std::cout (e.g. rrt/src/rrtplanner.cpp:345).  Inside a Python process that has
+  // loaded extension modules with a statically linked libstdc++ (numpy), the iostream locale facets resolve to
+  // foreign GNU-unique symbols and `cout << size_t` crashes; muting the stream skips the facet path.
+  std::cout.setstate(std::ios_base::failbit);
   set_launch_params();
   read_params();
   g_veh.setPrius();
@@ -302,6 +306,10 @@ double ref_rollout_batch(const int* parent, const double* sample_xy, const unsig
     const Node& p = g_rrt->tree[parent[j]];
     if (gb && gb[j]) {
       MyReference ref = getGoalReference(g_veh, p, g_rrt->goalPose);
+      // getGoalReference never sets ref.dir (rrt/src/reference.cpp:34-69): indeterminate upstream.  Inside
+      // expandTree the stack slot still holds the 1 written by the preceding getReference (verified: trees
+      // grown by the -O3 build match dir=1 bit-for-bit); called from here it would be garbage, so pin it.
+      ref.dir = 1;
       Simulation sim(*g_rrt, p.state, ref, g_veh, true, true, p.ref.v.back());
       fill_out(out + (size_t)OUT_STRIDE * j, sim, ref, c0, a0, i0);
     } else {
@@ -317,7 +325,7 @@ double ref_rollout_batch(const int* parent, const double* sample_xy, const unsig
 int ref_rollout_traj(int parent, const double* sample_xy, int gb, double* traj, int cap, double* refv, int vcap) {
   const Node& p = g_rrt->tree[parent];
   MyReference ref;
-  if (gb) ref = getGoalReference(g_veh, p, g_rrt->goalPose);
+  if (gb) { ref = getGoalReference(g_veh, p, g_rrt->goalPose); ref.dir = 1; }
   else { geometry_msgs::Point s; s.x = sample_xy[0]; s.y = sample_xy[1]; ref = getReference(s, p, 1); }
   Simulation sim(*g_rrt, p.state, ref, g_veh, gb != 0, true, p.ref.v.back());
   const int n = std::min<int>(cap, (int)sim.stateArray.size());

@@ -74,6 +74,10 @@ class CpuPlanner:
         obs = np.ascontiguousarray(obs, dtype=np.float64).reshape(-1, 7)
         self._f("set_obstacles")(_ptr(obs), C.c_int(len(obs)))
 
+    def set_tie_mode(self, mode):
+        """oracle only: 0 = equal keys ordered by node id (the product's rule), 1 = libstdc++ std::sort order."""
+        self._f("set_tie_mode")(C.c_int(mode))
+
     def set_weights(self, w5):
         w = np.ascontiguousarray(w5, dtype=np.float64)
         self._f("set_weights")(_ptr(w))
@@ -180,6 +184,30 @@ class CpuPlanner:
         ids = np.zeros(cap, dtype=np.int32)
         n = self._f("best_path")(_ptr(ids), C.c_int(cap))
         return ids[:min(n, cap)]
+
+
+def check_candidate_lists(planner, samples, heuristic, cand, key, cnt, limit=10):
+    """Specification check of top-`limit` feasible candidate lists (rrt/src/rrtplanner.cpp:227-268) that does not
+    depend on how equal keys are ordered (std::sort is unstable upstream): for every sample, with all keys and
+    feasibility flags recomputed by `planner` (oracle or reference):
+      count == min(limit, #feasible); every listed node is feasible and carries exactly its recomputed key;
+      listed keys are non-decreasing; no feasible node with a key strictly below the last listed key is missing.
+    Returns the number of samples checked."""
+    for j in range(len(samples)):
+        k_all, feas = planner.keys(samples[j], heuristic[j])
+        feas = feas.astype(bool)
+        n = int(cnt[j])
+        assert n == min(limit, int(feas.sum())), (j, n, int(feas.sum()))
+        ids = cand[j, :n]
+        assert len(set(ids.tolist())) == n and (cand[j, n:] == -1).all(), (j, cand[j])
+        assert feas[ids].all(), (j, ids)
+        assert np.array_equal(k_all[ids], key[j, :n]), (j, k_all[ids], key[j, :n])
+        assert (np.diff(key[j, :n]) >= 0).all(), (j, key[j, :n])
+        if n:
+            better = feas & (k_all < key[j, n - 1])
+            better[ids] = False
+            assert not better.any(), (j, np.where(better)[0])
+    return len(samples)
 
 
 # ---- the synthetic scenes of SURVEY.md §8d -----------------------------------------------------------

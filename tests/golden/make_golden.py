@@ -1,0 +1,162 @@
+"""Generate tests/golden/*.npz from the REFERENCE's own sources (oracle/_ref, built by oracle/build_ref.sh
+from /root/reference).  Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+Every array is produced by libclrrt_ref_defined.so (reference + the documented UB clamps) and
+cross-checked here against the unmodified libclrrt_ref.so on all untainted rollouts (bit-for-bit); the mask of
+rows where the unmodified build differs is stored as `unmod_differs` and must be a subset of `tainted`.
+Golden sets follow SURVEY.md §8c: G0 known answers, G1 rollouts (C2), G2 candidate lists, G3 whole-query
+replay at K=1, G4 dense-scene verdicts (C3).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from cpulib import (CpuPlanner, O_TAINT, scene_c1_boxes, scene_c3_boxes)  # noqa: E402
+
+NONE = np.zeros((0, 7))
+
+
+def fresh(kind, obs, car=(0, 0, 0, 0, 0, 0), goal=(50, 0, 0, 0), seed=1):
+    p = CpuPlanner(kind)
+    p.set_obstacles(obs)
+    p.srand(seed)
+    p.tree_init(car, goal, 5.0)
+    return p
+
+
+def rollouts_both(tree, obs, parent, samples, gb, car, goal):
+    """defined-variant outputs + mask of rows where the unmodified reference differs."""
+    outs = []
+    for kind in ("ref_defined", "ref"):
+        p = fresh(kind, obs, car, goal)
+        p.tree_import(tree)
+        outs.append(p.rollout_batch(parent, samples, gb))
+    d, u = outs
+    differs = (d != u).any(axis=1) & ~(np.isnan(d) & np.isnan(u)).all(axis=1)
+    tainted = d[:, O_TAINT] != 0
+    assert not (differs & ~tainted).any(), "unmodified reference differs on an untainted rollout"
+    return d, differs
+
+
+def g0():
+    p = CpuPlanner("ref")
+    kat = {
+        "obb_free": p.obb_dist([0, 0, 2, 5, 0], [3.55, 0, 2, 5, 1.57]),   # rrt/src/testers.cpp:132-133,158
+        "obb_hit": p.obb_dist([0, 0, 2, 5, 0], [3.55, 0, 2, 5, 2]),       # rrt/src/testers.cpp:134,159
+        "dubins_5_5_fwd": float(p.dubins(5, 5, 0, 0, 0, 1)),
+        "dubins_5_5_rev": float(p.dubins(5, 5, 0, 0, 0, -1)),
+        "dubins_1_1_in_circle": float(p.dubins(1, 1, 0, 0, 0, 1)),
+    }
+    p.set_obstacles([[10, 0, 0, 2, 4, 0, 0]])
+    xs = [0, 4, 5, 5.5, 6, 7, 8, 9, 10, 11, 12, 13, 13.5, 14, 16]
+    kat["vehicle_sweep_x"] = xs
+    kat["vehicle_sweep_dobs"] = [p.obs_distance([x, 0, 0, 0, 0, 0, 0, 0, 0, 0]) for x in xs]
+    p.set_obstacles(NONE)
+    p.srand(1)
+    p.tree_init()
+    s, h, r = p.draw_samples(3)
+    kat["first_samples"] = s.tolist()
+    kat["first_heuristic"] = h.tolist()
+    kat["first_r"] = r.tolist()
+    kat["prius"] = p.vehicle().tolist()
+    with open(os.path.join(HERE, "g0_kat.json"), "w") as f:
+        json.dump(kat, f, indent=1)
+    print("G0", kat["obb_free"], kat["dubins_5_5_fwd"], kat["vehicle_sweep_dobs"][:4])
+
+
+def g1_g2():
+    car, goal = (0, 0, 0, 0, 3, 0), (50, 0, 0, 0)
+    boxes = scene_c1_boxes()
+    # tree snapshots: one tree grown by the reference with the 10 boxes; snapshot N = its first N nodes
+    p = fresh("ref_defined", boxes, car, goal)
+    p.expand(60)
+    n60 = p.tree_size()
+    while p.tree_size() < 1500:
+        p.expand(50)
+    tree = p.tree_export()[:1500]
+    samples, heur, _ = p.draw_samples(4096)
+    # ---- G2: candidate lists for snapshots of 1, 64, 250, 1500 nodes --------------------------------
+    g2 = {"tree": tree, "samples": samples[:1024], "heuristic": heur[:1024], "n60": n60}
+    for N in (1, 64, 250, 1500):
+        q = fresh("ref_defined", boxes, car, goal)
+        q.tree_import(tree[:N])
+        cand, key, cnt = q.nearest_batch(samples[:1024], heur[:1024])
+        g2[f"cand_{N}"], g2[f"key_{N}"], g2[f"count_{N}"] = cand, key, cnt
+    np.savez_compressed(os.path.join(HERE, "g2_nearest.npz"), **g2)
+    print("G2 tree", tree.shape, "n60", n60, "counts", [int(g2[f"count_{N}"].sum()) for N in (1, 64, 250, 1500)])
+    # ---- G1: rollouts against the 60-iteration snapshot ----------------------------------------------
+    snap = tree[:n60]
+    q = fresh("ref_defined", boxes, car, goal)
+    q.tree_import(snap)
+    cand, key, cnt = q.nearest_batch(samples, heur)
+    par, smp, rank = [], [], []
+    for j in range(len(samples)):          # all (sample, candidate) pairs in reference order, first 4096
+        for r in range(cnt[j]):
+            par.append(cand[j, r]); smp.append(samples[j]); rank.append(r)
+    par, smp, rank = np.array(par[:4096], np.int32), np.array(smp[:4096]), np.array(rank[:4096], np.int32)
+    gb = np.zeros(len(par), np.uint8)
+    # root-only subset (parent 0) and goal-biased subset (every node as parent)
+    par_root = np.zeros(512, np.int32)
+    smp_root = samples[-512:]
+    par_gb = np.arange(n60, dtype=np.int32)
+    g1 = {"tree": snap, "car": np.array(car, float), "goal": np.array(goal, float), "obstacles": boxes}
+    for name, obs in (("obs", boxes), ("live", NONE)):
+        o, dif = rollouts_both(snap, obs, par, smp, gb, car, goal)
+        g1[f"out_{name}"], g1[f"unmod_differs_{name}"] = o, dif
+        o, dif = rollouts_both(snap, obs, par_root, smp_root, np.zeros(512, np.uint8), car, goal)
+        g1[f"out_root_{name}"], g1[f"unmod_differs_root_{name}"] = o, dif
+        o, dif = rollouts_both(snap, obs, par_gb, np.zeros((n60, 2)), np.ones(n60, np.uint8), car, goal)
+        g1[f"out_gb_{name}"], g1[f"unmod_differs_gb_{name}"] = o, dif
+        print("G1", name, "tainted", int(g1[f"out_{name}"][:, O_TAINT].sum()), "of", len(par),
+              "accepted", int(((g1[f"out_{name}"][:, 12] + g1[f"out_{name}"][:, 13]) > 0).sum()),
+              "unmod differs", int(g1[f"unmod_differs_{name}"].sum()),
+              "fail codes", np.bincount(g1[f"out_{name}"][:, 15].astype(int), minlength=4).tolist())
+    g1.update(parent=par, samples=smp, rank=rank, parent_root=par_root, samples_root=smp_root, parent_gb=par_gb)
+    np.savez_compressed(os.path.join(HERE, "g1_rollouts.npz"), **g1)
+
+
+def g3():
+    out = {}
+    for name, obs in (("live", NONE), ("obs", scene_c1_boxes())):
+        p = fresh("ref_defined", obs)
+        s, h, _ = p.draw_samples(200)       # the draws expandTree will make (3 rand() per iteration)
+        p.srand(1)
+        p.expand(200)
+        out[f"tree_{name}"] = p.tree_export()
+        out[f"counters_{name}"] = np.array(list(p.counters().values()))
+        out[f"best_{name}"] = p.best_path()
+        out["samples"], out["heuristic"] = s, h
+        u = fresh("ref", obs)
+        u.expand(1)
+        # node 1 of the live tree is the value quoted in SURVEY.md §8c (G3 row)
+        print("G3", name, "nodes", p.tree_size(), "node1", out[f"tree_{name}"][1, :3], p.counters())
+    np.savez_compressed(os.path.join(HERE, "g3_replay.npz"), **out)
+
+
+def g4():
+    car, goal = (0, 0, 0, 0, 3, 0), (100, 0, 0, 0)
+    boxes = scene_c3_boxes()
+    p = fresh("ref_defined", boxes, car, goal)
+    p.expand(400)
+    tree = p.tree_export()
+    samples, heur, _ = p.draw_samples(1024)
+    cand, key, cnt = p.nearest_batch(samples, heur)
+    ok = cnt > 0
+    par, smp = cand[ok, 0].astype(np.int32), samples[ok]
+    o, dif = rollouts_both(tree, boxes, par, smp, np.zeros(len(par), np.uint8), car, goal)
+    print("G4 tree", len(tree), "rollouts", len(par), "fail codes", np.bincount(o[:, 15].astype(int), minlength=4).tolist(),
+          "tainted", int(o[:, O_TAINT].sum()))
+    np.savez_compressed(os.path.join(HERE, "g4_dense.npz"), tree=tree, car=np.array(car, float), goal=np.array(goal, float),
+                        obstacles=boxes, parent=par, samples=smp, out=o, unmod_differs=dif)
+
+
+if __name__ == "__main__":
+    g0(); g1_g2(); g3(); g4()
+    for f in sorted(os.listdir(HERE)):
+        print(f, os.path.getsize(os.path.join(HERE, f)))
