@@ -1,0 +1,652 @@
+// clrrt_api.cu — the C ABI of include/clrrt.h: context, device buffers, kernel launches (sm_100a).
+// One translation unit (the kernels live in the .cuh files) so that the __constant__ parameter block is
+// shared by all kernels.  No CPU fallback: every entry point needs the CUDA device of its context.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "nearest.cuh"
+#include "rollout.cuh"
+#include "tree.cuh"
+
+namespace {
+
+struct RolloutScratch {
+  int cap = 0;
+  int32_t *d_parent = nullptr, *d_list0 = nullptr, *d_list1 = nullptr;
+  double* d_samples = nullptr;
+  clrrt_rollout* d_out = nullptr;
+  double* d_traj = nullptr;
+  size_t traj_cap = 0;
+};
+
+}  // namespace
+
+struct clrrt_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  clrrt_params prm;
+  DevParams dprm;
+  int cap = 0, max_round = 0, n_tree = 0;
+  NodeSoA tree{}, stage{};
+  void *tree_mem = nullptr, *stage_mem = nullptr;
+  ObsHot* d_hot = nullptr;
+  ObsCold* d_cold = nullptr;
+  ObsMoving* d_mov = nullptr;
+  int obs_cap = 0;
+  // round scratch
+  double* d_samples = nullptr;
+  uint8_t* d_heur = nullptr;
+  int32_t *d_cand = nullptr, *d_count = nullptr, *d_valid = nullptr, *d_gb_list = nullptr;
+  float* d_key = nullptr;
+  int32_t* d_ints = nullptr;  // [0] head main, [1] head gb, [2] gb_count, [3] total records, [4] best id
+  int32_t* d_block_sums = nullptr;
+  NodeRecord* d_records = nullptr;
+  unsigned long long* d_counters = nullptr;  // 8
+  int32_t* h_ints = nullptr;                 // pinned
+  unsigned long long* h_counters = nullptr;  // pinned
+  RolloutScratch batch;
+  cudaEvent_t ev[6]{};
+  int num_sms = 0, blocks_per_sm_main = 1, blocks_per_sm_gb = 1;
+  size_t smem_bytes = 0;
+  int refill_min = 1;
+  int blocks_override = 0;
+  bool defer_append = false;
+  int last_records = 0;
+  bool have_tree = false;
+  std::string err;
+};
+
+namespace {
+
+const clrrt_ctx* g_const_owner = nullptr;  // which context last uploaded c_prm on this process
+
+#define CK(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) {                                                                              \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                      \
+      return CLRRT_ERR_CUDA;                                                                              \
+    }                                                                                                     \
+  } while (0)
+
+int alloc_soa(clrrt_ctx* ctx, NodeSoA& s, void** mem, int n) {
+  const size_t nd = NODE_SOA_DOUBLE_FIELDS, nf = NODE_SOA_FLOAT_FIELDS, ni = NODE_SOA_INT_FIELDS;
+  const size_t n8 = ((size_t)n + 7) & ~(size_t)7;
+  const size_t bytes = n8 * (nd * 8 + nf * 4 + ni * 4);
+  CK(cudaMalloc(mem, bytes));
+  CK(cudaMemsetAsync(*mem, 0, bytes, ctx->stream));
+  double* d = reinterpret_cast<double*>(*mem);
+  double** df[] = {&s.x, &s.y, &s.th, &s.de, &s.v, &s.a, &s.t, &s.s7, &s.s8, &s.s9, &s.rfx, &s.rfy, &s.rbx, &s.rby, &s.vback, &s.angPar};
+  for (size_t i = 0; i < nd; i++) *df[i] = d + i * n8;
+  float* f = reinterpret_cast<float*>(d + nd * n8);
+  float** ff[] = {&s.costE, &s.costS, &s.ca, &s.sa};
+  for (size_t i = 0; i < nf; i++) *ff[i] = f + i * n8;
+  int32_t* q = reinterpret_cast<int32_t*>(f + nf * n8);
+  int32_t** qf[] = {&s.parent, &s.goal, &s.nref};
+  for (size_t i = 0; i < ni; i++) *qf[i] = q + i * n8;
+  return CLRRT_OK;
+}
+
+// host-side mirror of std::max semantics used by the reference's lookahead formulas
+inline double hmax(double a, double b) { return (a < b) ? b : a; }
+
+void fill_dev_params(clrrt_ctx* ctx) {
+  const clrrt_params& p = ctx->prm;
+  DevParams& d = ctx->dprm;
+  const int ns = d.n_static, nm = d.n_moving, sm = d.static_in_smem;
+  memset(&d, 0, sizeof d);
+  d.n_static = ns; d.n_moving = nm; d.static_in_smem = sm;
+  d.dmax = p.veh.dmax; d.ddmax = p.veh.ddmax; d.inv_Td = 1 / p.veh.Td; d.inv_Ta = 1 / p.veh.Ta;
+  d.amin = p.veh.amin; d.amax = p.veh.amax; d.L = p.veh.L; d.Vch = p.veh.Vch; d.Kus = p.veh.Kus;
+  d.sim_dt = p.sim_dt; d.mindla = p.ctrl_mindla; d.tla = p.ctrl_tla;
+  d.dla_c = p.ctrl_mindla - p.ctrl_tla * p.ctrl_dlavmin;  // controller.cpp:14
+  d.Kp = p.ctrl_Kp; d.Ki = p.ctrl_Ki; d.ref_res = p.ref_res; d.vmax = p.vmax; d.ay_road_max = p.ay_road_max;
+  for (int i = 0; i < 5; i++) d.W[i] = p.Wcost[i];
+  for (int i = 0; i < 4; i++) d.goal[i] = p.goal[i];
+  d.feas_len = 2.1 * p.ref_res;  // rrtplanner.cpp:283
+  // feasibleGoalBias, rrtplanner.cpp:294-299 (both centre coordinates use cos, as upstream)
+  const double R1 = 4.77, R2 = R1 - 0.3;
+  d.gb_clx = p.goal[0] + R1 * cos(p.goal[2] - M_PI_2);
+  d.gb_cly = p.goal[1] + R1 * cos(p.goal[2] - M_PI_2);
+  d.gb_crx = p.goal[0] + R1 * cos(p.goal[2] + M_PI_2);
+  d.gb_cry = p.goal[1] + R1 * cos(p.goal[2] + M_PI_2);
+  d.gb_R2 = R2;
+  // getGoalReference, reference.cpp:27-50
+  const double dla_end = hmax(p.ctrl_mindla, d.dla_c + p.ctrl_tla * std::fabs(p.goal[3]));
+  const double Dextend = dla_end, Dalign = 1;
+  d.gb_P1x = p.goal[0] + Dalign * cos(p.goal[2]); d.gb_P1y = p.goal[1] + Dalign * sin(p.goal[2]);
+  d.gb_P2x = p.goal[0] - Dalign * cos(p.goal[2]); d.gb_P2y = p.goal[1] - Dalign * sin(p.goal[2]);
+  d.gb_ext_x = (Dextend + Dalign) * cos(p.goal[2]);
+  d.gb_ext_y = (Dextend + Dalign) * sin(p.goal[2]);
+  // OBB vOBB(vPos, 2, 4.848, theta): float w, h (collision.h:24); setVertices uses w/2, h/2
+  const float vw = 2, vh = 4.848;
+  d.veh_hw = vw / 2; d.veh_hh = vh / 2;
+  int ms = 0;
+  while (ms < (20 / p.sim_dt) && ms < CLRRT_MAX_STEPS_CAP * 64) ms++;  // simulation.cpp:58
+  d.max_steps = ms;
+  d.obs_use_pred = p.obs_use_pred;
+}
+
+int upload_params(clrrt_ctx* ctx) {
+  CK(cudaMemcpyToSymbolAsync(c_prm, &ctx->dprm, sizeof(DevParams), 0, cudaMemcpyHostToDevice, ctx->stream));
+  g_const_owner = ctx;
+  return CLRRT_OK;
+}
+int ensure_params(clrrt_ctx* ctx) {
+  if (g_const_owner != ctx) return upload_params(ctx);
+  return CLRRT_OK;
+}
+
+int configure_launch(clrrt_ctx* ctx) {
+  ctx->smem_bytes = ctx->dprm.static_in_smem ? (size_t)ctx->dprm.n_static * sizeof(ObsHot) : 0;
+  CK(cudaFuncSetAttribute(rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+  CK(cudaFuncSetAttribute(rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+  int b0 = 1, b1 = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rollout_kernel<false>, ROLLOUT_THREADS, ctx->smem_bytes));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, rollout_kernel<true>, ROLLOUT_THREADS, ctx->smem_bytes));
+  ctx->blocks_per_sm_main = std::max(1, b0);
+  ctx->blocks_per_sm_gb = std::max(1, b1);
+  return CLRRT_OK;
+}
+
+template <bool GB> int launch_rollout(clrrt_ctx* ctx, const RolloutJob& job, int n_items_hint) {
+  int per_sm = GB ? ctx->blocks_per_sm_gb : ctx->blocks_per_sm_main;
+  if (ctx->blocks_override > 0) per_sm = std::min(per_sm, ctx->blocks_override);
+  const int lanes_per_block = ROLLOUT_THREADS;
+  int blocks = ctx->num_sms * per_sm;  // persistent grid: a multiple of the SM count
+  const int needed = (n_items_hint + lanes_per_block - 1) / lanes_per_block;
+  if (needed < blocks) blocks = std::max(1, needed);
+  rollout_kernel<GB><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_hot, ctx->d_cold, ctx->d_mov);
+  CK(cudaGetLastError());
+  return CLRRT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int clrrt_default_params(clrrt_params* p) {
+  if (!p) return CLRRT_ERR_ARG;
+  memset(p, 0, sizeof *p);
+  // Vehicle::setPrius(), rrt/include/rrt/vehicle.h:39-60
+  clrrt_vehicle& v = p->veh;
+  v.dmax = 0.52; v.ddmax = 0.3294; v.Td = 0.3; v.Ta = 0.3; v.amin = -6; v.amax = 2; v.L = 2.7;
+  const double lf = 1.0868, lr = 1.6132;
+  v.Lrear = 1; v.Lfront = 2.7 + 0.5; v.w = 2; v.b = lr; v.rho = 5.95;
+  const double Cf = 22201, Cr = 22201, m = 950 + 640;
+  v.Kus = (m / v.L) * (lr / Cf - lf / Cr);
+  v.Vch = 20;
+  // rrt/launch/parameters.launch:3-20
+  p->ctrl_tla = 1.4; p->ctrl_mindla = 3.2; p->ctrl_dlavmin = 3; p->ref_int = 0.02; p->ref_mindist = 0.2;
+  p->sim_dt = 0.04; p->ctrl_Kp = 8; p->ctrl_Ki = 0.05;
+  p->Wcost[0] = 10; p->Wcost[1] = 5; p->Wcost[2] = 0; p->Wcost[3] = 4; p->Wcost[4] = 1;
+  p->vmax = 5; p->ay_road_max = 0;
+  p->ref_res = hmax(std::fabs(0.0) * p->ref_int, p->ref_mindist);
+  p->goal[0] = 50; p->goal[1] = 0; p->goal[2] = 0; p->goal[3] = 0;
+  p->obs_use_pred = 1; p->fp32 = 0;
+  return CLRRT_OK;
+}
+
+int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_round, void* stream, clrrt_ctx** out) {
+  if (!p || !out || tree_capacity < 1 || max_round < 1) return CLRRT_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return CLRRT_ERR_CUDA;
+  clrrt_ctx* ctx = new clrrt_ctx();
+  ctx->device = device;
+  ctx->prm = *p;
+  ctx->cap = tree_capacity;
+  ctx->max_round = max_round;
+  memset(&ctx->dprm, 0, sizeof ctx->dprm);
+  auto fail = [&](int code) { *out = ctx; return code; };  // caller can read clrrt_last_error, then destroy
+  if (cudaSetDevice(device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return fail(CLRRT_ERR_CUDA); }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { ctx->err = "cudaGetDeviceProperties failed"; return fail(CLRRT_ERR_CUDA); }
+  ctx->num_sms = prop.multiProcessorCount;
+  if (stream) ctx->stream = (cudaStream_t)stream;
+  else {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(CLRRT_ERR_CUDA); }
+    ctx->own_stream = true;
+  }
+  int rc;
+  if ((rc = alloc_soa(ctx, ctx->tree, &ctx->tree_mem, tree_capacity)) != CLRRT_OK) return fail(rc);
+  if ((rc = alloc_soa(ctx, ctx->stage, &ctx->stage_mem, 2 * max_round)) != CLRRT_OK) return fail(rc);
+  auto mal = [&](void** ptr, size_t bytes) { return cudaMalloc(ptr, bytes) == cudaSuccess; };
+  const size_t K = (size_t)max_round;
+  bool ok = true;
+  ok &= mal((void**)&ctx->d_samples, K * 2 * sizeof(double));
+  ok &= mal((void**)&ctx->d_heur, K);
+  ok &= mal((void**)&ctx->d_cand, K * CLRRT_SORT_LIMIT * sizeof(int32_t));
+  ok &= mal((void**)&ctx->d_key, K * CLRRT_SORT_LIMIT * sizeof(float));
+  ok &= mal((void**)&ctx->d_count, K * sizeof(int32_t));
+  ok &= mal((void**)&ctx->d_valid, 2 * K * sizeof(int32_t));
+  ok &= mal((void**)&ctx->d_gb_list, K * sizeof(int32_t));
+  ok &= mal((void**)&ctx->d_ints, 16 * sizeof(int32_t));
+  ok &= mal((void**)&ctx->d_block_sums, ((K + SCAN_THREADS - 1) / SCAN_THREADS + 1) * sizeof(int32_t));
+  ok &= mal((void**)&ctx->d_records, 2 * K * sizeof(NodeRecord));
+  ok &= mal((void**)&ctx->d_counters, 8 * sizeof(unsigned long long));
+  ok &= cudaMallocHost((void**)&ctx->h_ints, 16 * sizeof(int32_t)) == cudaSuccess;
+  ok &= cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(unsigned long long)) == cudaSuccess;
+  if (!ok) { ctx->err = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()); return fail(CLRRT_ERR_CUDA); }
+  cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream);
+  cudaMemsetAsync(ctx->d_ints, 0, 16 * sizeof(int32_t), ctx->stream);
+  for (auto& e : ctx->ev) cudaEventCreate(&e);
+  fill_dev_params(ctx);
+  if ((rc = configure_launch(ctx)) != CLRRT_OK) return fail(rc);
+  if ((rc = upload_params(ctx)) != CLRRT_OK) return fail(rc);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "initial sync failed"; return fail(CLRRT_ERR_CUDA); }
+  *out = ctx;
+  return CLRRT_OK;
+}
+
+int clrrt_destroy(clrrt_ctx* ctx) {
+  if (!ctx) return CLRRT_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  void* ptrs[] = {ctx->tree_mem, ctx->stage_mem, ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_samples, ctx->d_heur,
+                  ctx->d_cand, ctx->d_key, ctx->d_count, ctx->d_valid, ctx->d_gb_list, ctx->d_ints, ctx->d_block_sums,
+                  ctx->d_records, ctx->d_counters, ctx->batch.d_parent, ctx->batch.d_list0, ctx->batch.d_list1,
+                  ctx->batch.d_samples, ctx->batch.d_out, ctx->batch.d_traj};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (ctx->h_ints) cudaFreeHost(ctx->h_ints);
+  if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+  for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (g_const_owner == ctx) g_const_owner = nullptr;
+  delete ctx;
+  return CLRRT_OK;
+}
+
+const char* clrrt_last_error(const clrrt_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int clrrt_get_device(const clrrt_ctx* ctx) { return ctx ? ctx->device : CLRRT_ERR_ARG; }
+
+int clrrt_set_params(clrrt_ctx* ctx, const clrrt_params* p) {
+  if (!ctx || !p) return CLRRT_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  ctx->prm = *p;
+  fill_dev_params(ctx);
+  return upload_params(ctx);
+}
+
+int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
+  if (!ctx || n < 0 || (n > 0 && !host)) return CLRRT_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  std::vector<ObsHot> hot;
+  std::vector<ObsCold> cold;
+  std::vector<ObsMoving> mov;
+  for (int i = 0; i < n; i++) {
+    const clrrt_obstacle& o = host[i];
+    // getOBBvector, old_collisioncheck.cpp:14-16: OBB(centre, size_x/2, size_y/2, theta) with float w, h, o
+    const float w = (float)(o.size_x / 2), h = (float)(o.size_y / 2), th = (float)o.theta;
+    const float co = cosf(th), so = sinf(th);  // the host libm: bit-identical to the reference's own calls
+    const float ch = co * (h / 2), sw = so * (w / 2), sh = so * (h / 2), cw = co * (w / 2);
+    if (o.vx == 0.0 && o.vy == 0.0) {
+      ObsHot a;
+      ObsCold c;
+      const double px = o.cx, py = o.cy;  // centre + 0*t
+      a.vx[0] = (float)((px + (double)ch) - (double)sw); a.vy[0] = (float)((py + (double)sh) + (double)cw);
+      a.vx[1] = (float)((px + (double)ch) + (double)sw); a.vy[1] = (float)((py + (double)sh) - (double)cw);
+      a.vx[2] = (float)((px - (double)ch) + (double)sw); a.vy[2] = (float)((py - (double)sh) - (double)cw);
+      a.vx[3] = (float)((px - (double)ch) - (double)sw); a.vy[3] = (float)((py - (double)sh) + (double)cw);
+      for (int k = 0; k < 3; k++) { c.nx[k] = a.vy[k + 1] - a.vy[k]; c.ny[k] = -(a.vx[k + 1] - a.vx[k]); }
+      c.nx[3] = -(a.vx[0] - a.vx[3]); c.ny[3] = 0.0f;
+      for (int k = 0; k < 4; k++) {
+        float mx = 0, mn = 0;
+        for (int q = 0; q < 4; q++) {
+          const float m1 = a.vx[q] * c.nx[k];
+          const float m2 = a.vy[q] * c.ny[k];
+          const float pr = m1 + m2;
+          if (q == 0) { mx = pr; mn = pr; }
+          else if (pr > mx) mx = pr;
+          else if (pr < mn) mn = pr;
+        }
+        c.pmax[k] = mx; c.pmin[k] = mn;
+      }
+      hot.push_back(a);
+      cold.push_back(c);
+    } else {
+      ObsMoving m;
+      m.cx = o.cx; m.cy = o.cy; m.vx = o.vx; m.vy = o.vy; m.ch = ch; m.sw = sw; m.sh = sh; m.cw = cw;
+      mov.push_back(m);
+    }
+  }
+  const int total = std::max<int>(1, n);
+  if (total > ctx->obs_cap) {
+    if (ctx->d_hot) cudaFree(ctx->d_hot);
+    if (ctx->d_cold) cudaFree(ctx->d_cold);
+    if (ctx->d_mov) cudaFree(ctx->d_mov);
+    ctx->d_hot = nullptr; ctx->d_cold = nullptr; ctx->d_mov = nullptr;
+    CK(cudaMalloc((void**)&ctx->d_hot, total * sizeof(ObsHot)));
+    CK(cudaMalloc((void**)&ctx->d_cold, total * sizeof(ObsCold)));
+    CK(cudaMalloc((void**)&ctx->d_mov, total * sizeof(ObsMoving)));
+    ctx->obs_cap = total;
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (!hot.empty()) {
+    CK(cudaMemcpy(ctx->d_hot, hot.data(), hot.size() * sizeof(ObsHot), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_cold, cold.data(), cold.size() * sizeof(ObsCold), cudaMemcpyHostToDevice));
+  }
+  if (!mov.empty()) CK(cudaMemcpy(ctx->d_mov, mov.data(), mov.size() * sizeof(ObsMoving), cudaMemcpyHostToDevice));
+  ctx->dprm.n_static = (int)hot.size();
+  ctx->dprm.n_moving = (int)mov.size();
+  // the hot table (32 B per obstacle) is staged in shared memory when it fits next to a second resident block
+  ctx->dprm.static_in_smem = (hot.size() * sizeof(ObsHot) <= 96 * 1024) ? 1 : 0;
+  int rc = configure_launch(ctx);
+  if (rc != CLRRT_OK) return rc;
+  return upload_params(ctx);
+}
+
+int clrrt_tree_reset(clrrt_ctx* ctx, const clrrt_node* host, int n) {
+  if (!ctx || !host || n < 1) return CLRRT_ERR_ARG;
+  if (n > ctx->cap) return CLRRT_ERR_CAPACITY;
+  CK(cudaSetDevice(ctx->device));
+  // route through the record path so that derived fields are produced by the same kernel as for appended nodes
+  std::vector<NodeRecord> rec((size_t)n);
+  for (int i = 0; i < n; i++) {
+    NodeRecord& r = rec[i];
+    memset(&r, 0, sizeof r);
+    memcpy(r.state, host[i].state, sizeof r.state);
+    r.rf[0] = host[i].ref_front[0]; r.rf[1] = host[i].ref_front[1];
+    r.rb[0] = host[i].ref_back[0]; r.rb[1] = host[i].ref_back[1];
+    r.vback = host[i].ref_vback; r.costE = host[i].costE; r.costS = host[i].costS;
+    r.parent = host[i].parent; r.goal = host[i].goal_reached; r.nref = host[i].n_ref; r.sample = -1;
+  }
+  NodeRecord* d_tmp = nullptr;
+  CK(cudaMalloc((void**)&d_tmp, (size_t)n * sizeof(NodeRecord)));
+  CK(cudaMemcpyAsync(d_tmp, rec.data(), (size_t)n * sizeof(NodeRecord), cudaMemcpyHostToDevice, ctx->stream));
+  append_records_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->tree, 0, d_tmp, n, ctx->cap);
+  CK(cudaGetLastError());
+  CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaFree(d_tmp));
+  ctx->n_tree = n;
+  ctx->have_tree = true;
+  return CLRRT_OK;
+}
+
+int clrrt_tree_size(const clrrt_ctx* ctx) { return ctx ? ctx->n_tree : CLRRT_ERR_ARG; }
+
+int clrrt_tree_truncate(clrrt_ctx* ctx, int n) {
+  if (!ctx || n < 1 || n > ctx->n_tree) return CLRRT_ERR_ARG;
+  ctx->n_tree = n;
+  return CLRRT_OK;
+}
+
+int clrrt_tree_download(clrrt_ctx* ctx, clrrt_node* host, int cap, int* n_out) {
+  if (!ctx || !host || cap < 0) return CLRRT_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const int n = std::min(cap, ctx->n_tree);
+  if (n_out) *n_out = n;
+  if (n == 0) return CLRRT_OK;
+  std::vector<double> d((size_t)n * 15);
+  std::vector<float> f((size_t)n * 2);
+  std::vector<int32_t> q((size_t)n * 3);
+  CK(cudaStreamSynchronize(ctx->stream));
+  const double* dsrc[15] = {ctx->tree.x, ctx->tree.y, ctx->tree.th, ctx->tree.de, ctx->tree.v, ctx->tree.a, ctx->tree.t,
+                            ctx->tree.s7, ctx->tree.s8, ctx->tree.s9, ctx->tree.rfx, ctx->tree.rfy, ctx->tree.rbx,
+                            ctx->tree.rby, ctx->tree.vback};
+  for (int k = 0; k < 15; k++) CK(cudaMemcpy(d.data() + (size_t)k * n, dsrc[k], (size_t)n * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(f.data(), ctx->tree.costE, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(f.data() + n, ctx->tree.costS, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(q.data(), ctx->tree.parent, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(q.data() + n, ctx->tree.goal, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(q.data() + 2 * (size_t)n, ctx->tree.nref, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; i++) {
+    clrrt_node& o = host[i];
+    for (int k = 0; k < 10; k++) o.state[k] = d[(size_t)k * n + i];
+    o.ref_front[0] = d[(size_t)10 * n + i]; o.ref_front[1] = d[(size_t)11 * n + i];
+    o.ref_back[0] = d[(size_t)12 * n + i]; o.ref_back[1] = d[(size_t)13 * n + i];
+    o.ref_vback = d[(size_t)14 * n + i];
+    o.costE = f[i]; o.costS = f[(size_t)n + i];
+    o.parent = q[i]; o.goal_reached = q[(size_t)n + i]; o.n_ref = q[2 * (size_t)n + i]; o.reserved = 0;
+  }
+  return CLRRT_OK;
+}
+
+static int nearest_dev(clrrt_ctx* ctx, const double* d_samples, const uint8_t* d_heur, int K, int32_t* d_cand,
+                       float* d_key, int32_t* d_count) {
+  NearestArgs a;
+  a.sample_xy = d_samples; a.heuristic = d_heur; a.K = K; a.n_nodes = ctx->n_tree; a.tree = ctx->tree;
+  a.cand = d_cand; a.key = d_key; a.count = d_count; a.feas_len = ctx->dprm.feas_len;
+  const int blocks = (K + NEAREST_WARPS - 1) / NEAREST_WARPS;
+  nearest_topk_kernel<<<blocks, NEAREST_THREADS, 0, ctx->stream>>>(a);
+  CK(cudaGetLastError());
+  return CLRRT_OK;
+}
+
+int clrrt_nearest_batch(clrrt_ctx* ctx, const double* sample_xy, const uint8_t* heuristic, int K, int32_t* cand,
+                        float* key, int32_t* count) {
+  if (!ctx || !sample_xy || !heuristic || !cand || !count || K < 1) return CLRRT_ERR_ARG;
+  if (!ctx->have_tree) return CLRRT_ERR_STATE;
+  if (K > ctx->max_round) return CLRRT_ERR_CAPACITY;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_params(ctx);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->d_samples, sample_xy, (size_t)K * 16, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_heur, heuristic, (size_t)K, cudaMemcpyHostToDevice, ctx->stream));
+  rc = nearest_dev(ctx, ctx->d_samples, ctx->d_heur, K, ctx->d_cand, ctx->d_key, ctx->d_count);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(cand, ctx->d_cand, (size_t)K * CLRRT_SORT_LIMIT * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (key) CK(cudaMemcpyAsync(key, ctx->d_key, (size_t)K * CLRRT_SORT_LIMIT * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(count, ctx->d_count, (size_t)K * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return CLRRT_OK;
+}
+
+int clrrt_propagate_batch(clrrt_ctx* ctx, const int32_t* parent, const double* sample_xy, const uint8_t* goal_biased,
+                          int M, clrrt_rollout* out, double* traj, int traj_stride) {
+  if (!ctx || !parent || !sample_xy || !out || M < 1) return CLRRT_ERR_ARG;
+  if (traj && traj_stride < 2) return CLRRT_ERR_ARG;
+  if (!ctx->have_tree) return CLRRT_ERR_STATE;
+  for (int i = 0; i < M; i++)
+    if (parent[i] < 0 || parent[i] >= ctx->n_tree) return CLRRT_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_params(ctx);
+  if (rc) return rc;
+  RolloutScratch& b = ctx->batch;
+  if (M > b.cap) {
+    void* ptrs[] = {b.d_parent, b.d_list0, b.d_list1, b.d_samples, b.d_out};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    CK(cudaMalloc((void**)&b.d_parent, (size_t)M * 4));
+    CK(cudaMalloc((void**)&b.d_list0, (size_t)M * 4));
+    CK(cudaMalloc((void**)&b.d_list1, (size_t)M * 4));
+    CK(cudaMalloc((void**)&b.d_samples, (size_t)M * 16));
+    CK(cudaMalloc((void**)&b.d_out, (size_t)M * sizeof(clrrt_rollout)));
+    b.cap = M;
+  }
+  const size_t traj_elems = traj ? (size_t)M * traj_stride * 10 : 0;
+  if (traj_elems > b.traj_cap) {
+    if (b.d_traj) cudaFree(b.d_traj);
+    CK(cudaMalloc((void**)&b.d_traj, traj_elems * 8));
+    b.traj_cap = traj_elems;
+  }
+  std::vector<int32_t> l0, l1;
+  for (int i = 0; i < M; i++) ((goal_biased && goal_biased[i]) ? l1 : l0).push_back(i);
+  CK(cudaMemcpyAsync(b.d_parent, parent, (size_t)M * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(b.d_samples, sample_xy, (size_t)M * 16, cudaMemcpyHostToDevice, ctx->stream));
+  if (!l0.empty()) CK(cudaMemcpyAsync(b.d_list0, l0.data(), l0.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (!l1.empty()) CK(cudaMemcpyAsync(b.d_list1, l1.data(), l1.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_ints, 0, 4 * sizeof(int32_t), ctx->stream));
+  if (traj) CK(cudaMemsetAsync(b.d_traj, 0, traj_elems * 8, ctx->stream));
+  RolloutJob job;
+  memset(&job, 0, sizeof job);
+  job.cand = b.d_parent; job.count = nullptr; job.cand_stride = 1; job.sample_xy = b.d_samples;
+  job.parents = ctx->tree; job.out_records = b.d_out; job.traj = traj ? b.d_traj : nullptr; job.traj_stride = traj_stride;
+  job.counters = ctx->d_counters; job.refill_min = ctx->refill_min;
+  if (!l0.empty()) {
+    job.n_items = (int)l0.size(); job.item_list = b.d_list0; job.head = ctx->d_ints + 0;
+    if ((rc = launch_rollout<false>(ctx, job, job.n_items))) return rc;
+  }
+  if (!l1.empty()) {
+    job.n_items = (int)l1.size(); job.item_list = b.d_list1; job.head = ctx->d_ints + 1;
+    if ((rc = launch_rollout<true>(ctx, job, job.n_items))) return rc;
+  }
+  CK(cudaMemcpyAsync(out, b.d_out, (size_t)M * sizeof(clrrt_rollout), cudaMemcpyDeviceToHost, ctx->stream));
+  if (traj) CK(cudaMemcpyAsync(traj, b.d_traj, traj_elems * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return CLRRT_OK;
+}
+
+static int append_local(clrrt_ctx* ctx, const NodeRecord* d_rec, int n) {
+  if (n <= 0) return CLRRT_OK;
+  if (ctx->n_tree + n > ctx->cap) { ctx->err = "tree capacity exceeded"; return CLRRT_ERR_CAPACITY; }
+  append_records_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->tree, ctx->n_tree, d_rec, n, ctx->cap);
+  CK(cudaGetLastError());
+  ctx->n_tree += n;
+  return CLRRT_OK;
+}
+
+int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint8_t* d_heuristic, int K,
+                           clrrt_round_stats* stats) {
+  if (!ctx || !d_sample_xy || !d_heuristic || K < 1) return CLRRT_ERR_ARG;
+  if (!ctx->have_tree) return CLRRT_ERR_STATE;
+  if (K > ctx->max_round) return CLRRT_ERR_CAPACITY;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_params(ctx);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  CK(cudaEventRecord(ctx->ev[0], st));
+  // 1. candidate parents
+  if ((rc = nearest_dev(ctx, d_sample_xy, d_heuristic, K, ctx->d_cand, nullptr, ctx->d_count))) return rc;
+  CK(cudaEventRecord(ctx->ev[1], st));
+  // 2. rollouts in candidate order until the first success
+  CK(cudaMemsetAsync(ctx->d_ints, 0, 4 * sizeof(int32_t), st));
+  CK(cudaMemsetAsync(ctx->d_valid, 0, 2 * (size_t)K * sizeof(int32_t), st));
+  CK(cudaMemcpyAsync(ctx->h_counters + 8, ctx->d_counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  RolloutJob job;
+  memset(&job, 0, sizeof job);
+  job.n_items = K; job.head = ctx->d_ints + 0; job.cand = ctx->d_cand; job.count = ctx->d_count;
+  job.cand_stride = CLRRT_SORT_LIMIT; job.sample_xy = d_sample_xy; job.parents = ctx->tree;
+  job.out_nodes = ctx->stage; job.out_offset = 0; job.out_valid = ctx->d_valid;
+  job.gb_list = ctx->d_gb_list; job.gb_count = ctx->d_ints + 2;
+  job.counters = ctx->d_counters; job.refill_min = ctx->refill_min;
+  if ((rc = launch_rollout<false>(ctx, job, K))) return rc;
+  CK(cudaEventRecord(ctx->ev[2], st));
+  // 3. goal-biased rollout from every node just accepted that passes feasibleGoalBias
+  CK(cudaMemcpyAsync(ctx->h_ints + 2, ctx->d_ints + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const int n_gb = ctx->h_ints[2];
+  if (n_gb > 0) {
+    RolloutJob g;
+    memset(&g, 0, sizeof g);
+    g.n_items = n_gb; g.head = ctx->d_ints + 1; g.item_list = ctx->d_gb_list; g.parents = ctx->stage;
+    g.parent_offset = 0; g.parent_is_staged = 1; g.out_nodes = ctx->stage; g.out_offset = K; g.out_valid = ctx->d_valid;
+    g.counters = ctx->d_counters; g.refill_min = ctx->refill_min;
+    if ((rc = launch_rollout<true>(ctx, g, n_gb))) return rc;
+  }
+  CK(cudaEventRecord(ctx->ev[3], st));
+  // 4. compaction in sample order -> records -> append
+  const int nblocks = (K + SCAN_THREADS - 1) / SCAN_THREADS;
+  scan_block_sums_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(ctx->d_valid, K, ctx->d_block_sums);
+  scan_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(ctx->d_block_sums, nblocks, ctx->d_ints + 3);
+  pack_records_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(ctx->stage, ctx->d_valid, K, ctx->d_block_sums, ctx->d_records, 0);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->h_ints + 3, ctx->d_ints + 3, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const int n_new = ctx->h_ints[3];
+  ctx->last_records = n_new;
+  if (!ctx->defer_append) {
+    if ((rc = append_local(ctx, ctx->d_records, n_new))) return rc;
+  }
+  CK(cudaEventRecord(ctx->ev[4], st));
+  CK(cudaEventSynchronize(ctx->ev[4]));
+  if (stats) {
+    memset(stats, 0, sizeof *stats);
+    stats->samples = K;
+    stats->rollouts = (int32_t)(ctx->h_counters[4] - ctx->h_counters[12]);
+    stats->sim_steps = (int64_t)(ctx->h_counters[3] - ctx->h_counters[11]);
+    stats->nodes_added = n_new;
+    stats->tree_size = ctx->n_tree;
+    cudaEventElapsedTime(&stats->ms_nearest, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&stats->ms_rollout, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&stats->ms_goal, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&stats->ms_append, ctx->ev[3], ctx->ev[4]);
+  }
+  return CLRRT_OK;
+}
+
+int clrrt_expand_round(clrrt_ctx* ctx, const double* sample_xy, const uint8_t* heuristic, int K,
+                       clrrt_round_stats* stats) {
+  if (!ctx || !sample_xy || !heuristic || K < 1) return CLRRT_ERR_ARG;
+  if (K > ctx->max_round) return CLRRT_ERR_CAPACITY;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->d_samples, sample_xy, (size_t)K * 16, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_heur, heuristic, (size_t)K, cudaMemcpyHostToDevice, ctx->stream));
+  return clrrt_expand_round_dev(ctx, ctx->d_samples, ctx->d_heur, K, stats);
+}
+
+int clrrt_best_path(clrrt_ctx* ctx, int32_t* ids, int cap, int* n_out) {
+  if (!ctx || !ids || !n_out || cap < 1) return CLRRT_ERR_ARG;
+  if (!ctx->have_tree) return CLRRT_ERR_STATE;
+  CK(cudaSetDevice(ctx->device));
+  best_goal_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->tree, ctx->n_tree, ctx->d_ints + 4);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->h_ints + 4, ctx->d_ints + 4, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const int best = ctx->h_ints[4];
+  *n_out = 0;
+  if (best < 0) return CLRRT_OK;
+  // back-tracking (rrtplanner.cpp:351-358) over the parent array
+  std::vector<int32_t> par((size_t)ctx->n_tree);
+  CK(cudaMemcpy(par.data(), ctx->tree.parent, (size_t)ctx->n_tree * 4, cudaMemcpyDeviceToHost));
+  std::vector<int32_t> chain;
+  for (int id = best; id >= 0 && (int)chain.size() <= ctx->n_tree; id = par[id]) chain.push_back(id);
+  std::reverse(chain.begin(), chain.end());
+  *n_out = (int)chain.size();
+  for (int i = 0; i < std::min<int>(cap, (int)chain.size()); i++) ids[i] = chain[i];
+  return CLRRT_OK;
+}
+
+int clrrt_counters_get(clrrt_ctx* ctx, clrrt_counters* out) {
+  if (!ctx || !out) return CLRRT_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  out->fail_collision = (int64_t)ctx->h_counters[0];
+  out->fail_acclimit = (int64_t)ctx->h_counters[1];
+  out->fail_iterlimit = (int64_t)ctx->h_counters[2];
+  out->sim_count = (int64_t)ctx->h_counters[3];
+  out->rollouts = (int64_t)ctx->h_counters[4];
+  return CLRRT_OK;
+}
+
+int clrrt_set_tuning(clrrt_ctx* ctx, int refill_min, int blocks_per_sm) {
+  if (!ctx || refill_min < 1 || refill_min > 32 || blocks_per_sm < 0) return CLRRT_ERR_ARG;
+  ctx->refill_min = refill_min;
+  ctx->blocks_override = blocks_per_sm;
+  return CLRRT_OK;
+}
+
+int clrrt_set_defer_append(clrrt_ctx* ctx, int defer) {
+  if (!ctx) return CLRRT_ERR_ARG;
+  ctx->defer_append = defer != 0;
+  return CLRRT_OK;
+}
+int clrrt_round_records(clrrt_ctx* ctx, void** d_records, int* n_records) {
+  if (!ctx || !d_records || !n_records) return CLRRT_ERR_ARG;
+  *d_records = ctx->d_records;
+  *n_records = ctx->last_records;
+  return CLRRT_OK;
+}
+int clrrt_append_records(clrrt_ctx* ctx, const void* d_records, const int32_t* counts, int world, int stride_records) {
+  if (!ctx || !d_records || !counts || world < 1 || stride_records < 0) return CLRRT_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const NodeRecord* base = reinterpret_cast<const NodeRecord*>(d_records);
+  for (int r = 0; r < world; r++) {
+    int rc = append_local(ctx, base + (size_t)r * stride_records, counts[r]);
+    if (rc) return rc;
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return CLRRT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+/* clrrt.h — C ABI of the B200-native CL-RRT tree-expansion path (libclrrt_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of vdBerg93/cl-rrt:
+ *   MotionPlanner::planMotion -> expandTree -> Simulation (ctor + propagate)
+ * with nearest-node selection (sortNodesExplore / sortNodesOptimize) and the per-step OBB/SAT
+ * collision check.  The reference has no FFI of its own (it is one C++ translation unit); each entry
+ * point below names the reference interface it replaces (paths relative to the reference checkout).
+ * INTEGRATION.md shows the few lines a maintainer adds to rrt/src to call these instead.
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 or a negative clrrt_status; nothing
+ * is thrown across the boundary; the caller owns all host buffers, the context owns all device memory
+ * and its stream; calls on one context are not thread-safe (the reference is single-threaded and keeps
+ * its state in file-scope globals), distinct contexts are independent; one context per GPU.
+ * There is NO CPU fallback: without a CUDA device clrrt_create fails with CLRRT_ERR_CUDA.
+ */
+#ifndef CLRRT_H
+#define CLRRT_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLRRT_SORT_LIMIT 10   /* MyRRT::sortLimit, rrt/src/rrtplanner.cpp:13 */
+#define CLRRT_MAX_STEPS_CAP 1024
+
+typedef enum clrrt_status {
+  CLRRT_OK = 0,
+  CLRRT_ERR_ARG = -1,      /* null pointer / negative size / index out of range */
+  CLRRT_ERR_CUDA = -2,     /* CUDA runtime error; text in clrrt_last_error() */
+  CLRRT_ERR_CAPACITY = -3, /* tree or scratch capacity exceeded */
+  CLRRT_ERR_STATE = -4     /* call order (e.g. expand before tree_reset) */
+} clrrt_status;
+
+/* Vehicle, rrt/include/rrt/vehicle.h:5-21 (same field order). */
+typedef struct clrrt_vehicle {
+  double dmax, ddmax, Td, Ta, amin, amax, L, w, Lrear, Lfront, b, Vch, rho, Kus;
+} clrrt_vehicle;
+
+/* Everything the reference keeps in file-scope globals (rrt/src/rrt_node.cpp:2-24), ROS parameters
+ * (rrt/launch/parameters.launch:3-20) and MyRRT members (rrt/include/rrt/rrtplanner.h:51-67). */
+typedef struct clrrt_params {
+  clrrt_vehicle veh;
+  double sim_dt;        /* ctrl/sampleTime */
+  double ctrl_tla, ctrl_mindla, ctrl_dlavmin, ctrl_Kp, ctrl_Ki;
+  double ref_int, ref_mindist;
+  double ref_res;       /* updateReferenceResolution(v), rrt/src/controller.cpp:18-21; set per query */
+  double vmax;          /* MotionRequest.vmax, rrt/src/motionplanner.cpp:17 */
+  double ay_road_max;   /* rrt/src/rrt_node.cpp:18 (never assigned upstream: 0) */
+  double Wcost[5];      /* MyRRT::Wcost, rrt/src/rrtplanner.cpp:14-18 */
+  double goal[4];       /* MyRRT::goalPose = MotionRequest.goal: x, y, heading, v */
+  int32_t obs_use_pred; /* rrt/src/rrt_node.cpp:11 */
+  int32_t fp32;         /* 0: reference arithmetic (double rollout, float geometry); 1: float rollout */
+} clrrt_params;
+
+/* car_msgs/msg/Obstacle2D.msg: vision_msgs/BoundingBox2D obb {center{x,y,theta}, size_x, size_y} + vel.linear */
+typedef struct clrrt_obstacle {
+  double cx, cy, theta, size_x, size_y, vx, vy;
+} clrrt_obstacle;
+
+/* One tree node: the fields of struct Node (rrt/include/rrt/rrtplanner.h:35-47) the hot path reads.
+ * ref_front/ref_back are ref.{x,y}.front()/back(), ref_vback is ref.v.back().  Trajectories (Node::tra)
+ * are not kept on the device; clrrt_propagate_batch re-materialises them on request. */
+typedef struct clrrt_node {
+  double state[10];   /* x y theta delta v a t IDwp vref dcmd, rrt/src/motionplanner.cpp:90, simulation.cpp:64-67 */
+  double ref_front[2];
+  double ref_back[2];
+  double ref_vback;
+  float costE, costS; /* stored as float upstream, rrtplanner.h:40-41 */
+  int32_t parent;     /* parentID, -1 for the root */
+  int32_t goal_reached;
+  int32_t n_ref;      /* ref.x.size() */
+  int32_t reserved;
+} clrrt_node;
+
+/* Result of one Simulation (rrt/include/rrt/simulation.h:11-17) plus what expandTree derives from it. */
+typedef struct clrrt_rollout {
+  double state[10];   /* stateArray.back() */
+  double costE, costS;
+  double ref_back[2]; /* ref.x.back(), ref.y.back() of the generated reference */
+  double ref_vback;   /* ref.v.back() after generateVelocityProfile */
+  double trace;       /* sum over steps i=1.. of i*IDwp_i (checksum of the waypoint trace) */
+  int32_t end_reached, goal_reached;
+  int32_t n_steps;    /* iterations of the loop at rrt/src/simulation.cpp:58 */
+  int32_t fail;       /* 0 none, 1 collision (:85), 2 lateral acceleration (:102), 3 iteration limit (:142) */
+  int32_t n_ref;      /* reference points */
+  int32_t idwp0;      /* waypoint chosen by the Controller ctor (stateArray[0][7]) */
+  int32_t tainted;    /* some step used IDwp >= n_ref-2: the unmodified reference reads out of bounds there */
+  int32_t reserved;
+} clrrt_rollout;
+
+/* Failure counters of rrt/src/rrt_node.cpp:21-24, accumulated since the last clrrt_tree_reset. */
+typedef struct clrrt_counters {
+  int64_t fail_collision, fail_acclimit, fail_iterlimit, sim_count;
+  int64_t rollouts;      /* Simulation constructions */
+} clrrt_counters;
+
+typedef struct clrrt_round_stats {
+  int32_t samples, rollouts, nodes_added, goal_nodes_added, tree_size;
+  int32_t reserved;
+  int64_t sim_steps;
+  float ms_nearest, ms_rollout, ms_goal, ms_append; /* device time per phase (CUDA events on the ctx stream) */
+} clrrt_round_stats;
+
+typedef struct clrrt_ctx clrrt_ctx;
+
+/* Launch-file parameters + Vehicle::setPrius() (rrt/src/motionplanner.cpp:13, rrt/include/rrt/vehicle.h:39-60),
+ * goal (50,0,0,0), vmax 5. */
+int clrrt_default_params(clrrt_params* p);
+
+/* Context: device buffers for a tree of up to tree_capacity nodes and rounds of up to max_round samples.
+ * `stream` is a cudaStream_t to launch on (NULL: the context creates its own). */
+int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_round, void* stream, clrrt_ctx** out);
+int clrrt_destroy(clrrt_ctx* ctx);
+const char* clrrt_last_error(const clrrt_ctx* ctx);
+
+/* Start-of-query updates: vmax/goal/ref_res/lookahead of rrt/src/motionplanner.cpp:16-17, weights of
+ * rrt/src/rrtplanner.cpp:14-18. */
+int clrrt_set_params(clrrt_ctx* ctx, const clrrt_params* p);
+
+/* == MotionPlanner::updateObstacles (rrt/src/motionplanner.cpp:81-86): replaces the obstacle set `det` that
+ * checkObsDistance (rrt/src/old_collisioncheck.cpp:24-51) tests after every sim step.  n == 0 gives the shipped
+ * stub behaviour (rrt/src/collisioncheck.cpp:6-8: distance 100, never a collision). */
+int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n);
+
+/* == the result of initializeTree (rrt/src/rrtplanner.cpp:39-95): upload the initial tree (root node, or the
+ * carried-over chain) and zero the counters. */
+int clrrt_tree_reset(clrrt_ctx* ctx, const clrrt_node* host, int n);
+int clrrt_tree_size(const clrrt_ctx* ctx);
+int clrrt_tree_truncate(clrrt_ctx* ctx, int n); /* drop nodes >= n (bench: same snapshot every round) */
+int clrrt_tree_download(clrrt_ctx* ctx, clrrt_node* host, int cap, int* n);
+
+/* == sortNodesExplore (heuristic[j]==0) / sortNodesOptimize (==1), rrt/src/rrtplanner.cpp:227-268, for K samples
+ * against the current tree: up to CLRRT_SORT_LIMIT feasible node ids in increasing key order (ties: lower id),
+ * padded with -1; key = float Dubins distance (+ float costE); count = list length. */
+int clrrt_nearest_batch(clrrt_ctx* ctx, const double* sample_xy, const uint8_t* heuristic, int K,
+                        int32_t* cand, float* key, int32_t* count);
+
+/* == M times { getReference / getGoalReference + Simulation::Simulation } (rrt/src/rrtplanner.cpp:151-152 when
+ * goal_biased[j]==0, :165-166 when 1; rrt/src/simulation.cpp:36-143) from tree node parent[j] towards sample j.
+ * traj (optional, may be NULL) receives stateArray: M x traj_stride x 10 doubles, rows 0..n_steps. */
+int clrrt_propagate_batch(clrrt_ctx* ctx, const int32_t* parent, const double* sample_xy,
+                          const uint8_t* goal_biased, int M, clrrt_rollout* out, double* traj, int traj_stride);
+
+/* == K iterations of expandTree (rrt/src/rrtplanner.cpp:123-174) against ONE tree snapshot: candidate search,
+ * rollouts in candidate order until the first success, goal-biased rollout from the node just added, append in
+ * sample order.  K == 1 is the reference's sequential algorithm exactly. */
+int clrrt_expand_round(clrrt_ctx* ctx, const double* sample_xy, const uint8_t* heuristic, int K,
+                       clrrt_round_stats* stats);
+/* Same, samples already resident in device memory (bench: inputs in HBM before the timed region). */
+int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint8_t* d_heuristic, int K,
+                           clrrt_round_stats* stats);
+
+/* == extractBestPath (rrt/src/rrtplanner.cpp:318-368): ids root..leaf of the cheapest (float costS) goal-reaching
+ * branch; *n = 0 when no node reached the goal. */
+int clrrt_best_path(clrrt_ctx* ctx, int32_t* ids, int cap, int* n);
+
+int clrrt_counters_get(clrrt_ctx* ctx, clrrt_counters* out);
+
+/* Multi-GPU (one context per rank): after a round run with append deferred, the nodes accepted by this rank are
+ * exposed as fixed-stride records for an all-gather (NCCL), and the gathered records of all ranks are appended
+ * in rank order == global sample order, so every rank ends with the same tree for any world size. */
+#define CLRRT_RECORD_BYTES 160
+int clrrt_set_defer_append(clrrt_ctx* ctx, int defer);
+int clrrt_round_records(clrrt_ctx* ctx, void** d_records, int* n_records);
+int clrrt_append_records(clrrt_ctx* ctx, const void* d_records, const int32_t* counts, int world, int stride_records);
+
+int clrrt_get_device(const clrrt_ctx* ctx);
+/* Launch tuning of the rollout kernel: refill_min = idle lanes a warp accumulates before it fetches new work
+ * (1 = refill immediately); blocks_per_sm = resident blocks of the persistent grid (0 = occupancy maximum). */
+int clrrt_set_tuning(clrrt_ctx* ctx, int refill_min, int blocks_per_sm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLRRT_H */

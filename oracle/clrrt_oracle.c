@@ -464,6 +464,7 @@ static int pair_cmp(const void* a, const void* b) {
  *               tie order of the reference binary built in this container; used to pin the oracle against
  *               whole-tree growth of the reference for arbitrary seeds (tests/test_oracle_vs_reference.py). */
 static int tie_mode = 0;
+static int n_search = -1; /* nodes visible to the candidate search; -1 = whole tree (snapshot rounds set it) */
 #define LESS(a, b) ((a).key < (b).key)
 static void sl_swap(orc_pair* a, orc_pair* b) { orc_pair t = *a; *a = *b; *b = t; }
 static void sl_unguarded_linear_insert(orc_pair* last) {
@@ -554,16 +555,17 @@ static void libstdcxx_sort(orc_pair* first, long n) {
 }
 /* sortNodesExplore :227-247 (heuristic 0) / sortNodesOptimize :250-268 (heuristic 1) */
 static int sortNodes(double sx, double sy, int heuristic, int* out, float* keyout) {
-  orc_pair* d = malloc(sizeof(orc_pair) * (size_t)n_tree);
-  for (int i = 0; i < n_tree; i++) {
+  const int n_vis = n_search >= 0 ? n_search : n_tree;
+  orc_pair* d = malloc(sizeof(orc_pair) * (size_t)n_vis);
+  for (int i = 0; i < n_vis; i++) {
     d[i].id = i;
     float k = dubinsDistance(sx, sy, tree[i].state, 1);
     d[i].key = heuristic ? tree[i].costE + k : k;
   }
-  if (tie_mode == 1) libstdcxx_sort(d, n_tree);
-  else qsort(d, (size_t)n_tree, sizeof(orc_pair), pair_cmp);
+  if (tie_mode == 1) libstdcxx_sort(d, n_vis);
+  else qsort(d, (size_t)n_vis, sizeof(orc_pair), pair_cmp);
   int n = 0;
-  for (int i = 0; i < n_tree; i++) {
+  for (int i = 0; i < n_vis; i++) {
     if (feasibleNode(&tree[d[i].id], sx, sy)) {
       out[n] = d[i].id;
       if (keyout) keyout[n] = d[i].key;
@@ -745,6 +747,15 @@ int orc_expand_timed(double budget_ms, int* iters_out) {
 /* expandTree with caller-supplied samples (K=1 sequential semantics, one sample after the other) */
 int orc_expand_with(const double* sample_xy, const unsigned char* heuristic, int K) {
   for (int j = 0; j < K; j++) expandTreeWith(sample_xy[2 * j], sample_xy[2 * j + 1], heuristic[j]);
+  return n_tree;
+}
+/* A round of K samples against ONE tree snapshot (the batched formulation of the GPU product, SURVEY.md §0
+   fact 4): every sample sees only the nodes present when the round started; accepted nodes (and their goal-biased
+   children) are appended in sample order.  K == 1 is expandTree itself. */
+int orc_expand_round(const double* sample_xy, const unsigned char* heuristic, int K) {
+  n_search = n_tree;
+  for (int j = 0; j < K; j++) expandTreeWith(sample_xy[2 * j], sample_xy[2 * j + 1], heuristic[j]);
+  n_search = -1;
   return n_tree;
 }
 int orc_tree_size(void) { return n_tree; }

@@ -104,6 +104,18 @@ class CpuPlanner:
         n = self._f("expand_timed")(C.c_double(budget_ms), C.byref(it))
         return n, it.value
 
+    def expand_with(self, samples, heuristic):
+        """oracle only: expandTree per sample, sequentially (K=1 semantics), with caller-supplied draws."""
+        s = np.ascontiguousarray(samples, dtype=np.float64).reshape(-1, 2)
+        h = np.ascontiguousarray(heuristic, dtype=np.uint8)
+        return self._f("expand_with")(_ptr(s), _ptr(h), C.c_int(len(s)))
+
+    def expand_round(self, samples, heuristic):
+        """oracle only: all samples against one tree snapshot, appended in sample order."""
+        s = np.ascontiguousarray(samples, dtype=np.float64).reshape(-1, 2)
+        h = np.ascontiguousarray(heuristic, dtype=np.uint8)
+        return self._f("expand_round")(_ptr(s), _ptr(h), C.c_int(len(s)))
+
     def tree_size(self):
         return self._f("tree_size")()
 
