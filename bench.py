@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py — CL-RRT tree-expansion throughput on B200 (contract in the task statement, tier section ④).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU code (oracle/_ref)
+
+A *step* is one expansion round: 65 536 samples (per GPU) against a fixed 4096-node tree snapshot in the dense
+urban scene (config C3: 1000 oriented-box obstacles, goal 100 m ahead): candidate search, closed-loop rollouts in
+candidate order until the first success, goal-biased rollouts, ordered append (+ node all-gather when N > 1).
+The tree is truncated back to the snapshot after every round so that each step does the same work.
+Metric: closed-loop sim steps per second (one sim step = one iteration of rrt/src/simulation.cpp:58), whole job.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "closed_loop_sim_steps_per_s"
+UNIT = "sim-steps/s"
+WORKLOAD = "C3 dense urban scene: 1000 OBB obstacles, 65536 samples/round/GPU, 4096-node tree snapshot, fp64 parity mode"
+K_ROUND = 65536
+TREE_SNAPSHOT = 4096
+CAR = (0.0, 0.0, 0.0, 0.0, 3.0, 0.0)
+GOAL = (100.0, 0.0, 0.0, 0.0)
+VMAX = 5.0
+
+
+def scene_c3_boxes():
+    """closed-form layout, no RNG."""
+    o = np.zeros((1000, 7))
+    for i in range(1000):
+        c, r = i % 100, i // 100
+        y = 3.0 + 1.5 * (r // 2)
+        o[i] = [5.0 + c, y if r % 2 == 0 else -y, (0.1 * i) % np.pi, 2.0, 4.0, 0.0, 0.0]
+    return o
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def build_workload(pl, clrrt, rank, world):
+    """Scene, tree snapshot (grown on the GPU with this library, deterministic) and the per-rank sample shards."""
+    boxes = scene_c3_boxes()
+    pl.set_query(CAR, GOAL, VMAX)
+    pl.set_obstacles(boxes)
+    pl.tree_reset(clrrt.root_node(CAR))
+    s, h = clrrt.draw_samples(GOAL, 8192 * 12, seed=1)
+    i = 0
+    while pl.tree_size() < TREE_SNAPSHOT and i < 12:
+        pl.expand_round(s[i * 8192:(i + 1) * 8192], h[i * 8192:(i + 1) * 8192])
+        i += 1
+    if pl.tree_size() < TREE_SNAPSHOT:
+        raise RuntimeError(f"tree snapshot only reached {pl.tree_size()} nodes")
+    pl.tree_truncate(TREE_SNAPSHOT)
+    # every rank draws the global stream and keeps its contiguous shard
+    gs, gh = clrrt.draw_samples(GOAL, K_ROUND * world, seed=2)
+    return boxes, gs[rank * K_ROUND:(rank + 1) * K_ROUND].copy(), gh[rank * K_ROUND:(rank + 1) * K_ROUND].copy()
+
+
+def cpu_baseline_sample(boxes, tree_records, samples, heur, budget_s=12.0, kind=None):
+    """The reference's own CPU code (oracle/_ref when present, else the C restatement) on a bounded sample of the
+    same workload: top-1 candidate rollouts, batches of 32 until the time budget is spent."""
+    from cpulib import CpuPlanner, ref_available
+    kind = kind or ("ref_defined" if ref_available(True) else "oracle")
+    cpu = CpuPlanner(kind)
+    cpu.set_obstacles(boxes)
+    cpu.tree_init(CAR, GOAL, VMAX)
+    cpu.tree_import(tree_records)
+    steps = rollouts = 0
+    secs = 0.0
+    t_nn = 0.0
+    j = 0
+    R_scan = A_axes = None
+    while secs + t_nn < budget_s and j + 32 <= len(samples):
+        cand, _, cnt = cpu.nearest_batch(samples[j:j + 32], heur[j:j + 32])
+        t_nn += cpu.last_seconds
+        ok = cnt > 0
+        out = cpu.rollout_batch(cand[ok, 0], samples[j:j + 32][ok])
+        secs += cpu.last_seconds
+        steps += int(out[:, 14].sum())
+        rollouts += int(ok.sum())
+        j += 32
+    return {"value": steps / max(secs + t_nn, 1e-9), "unit": UNIT, "cores": 1,
+            "kind": "reference" if kind.startswith("ref") else "port",
+            "sample": f"{rollouts} top-1 candidate rollouts ({steps} sim steps) + their candidate search for {j} samples "
+                      f"of the same round, {secs + t_nn:.1f} s on 1 host core ({'oracle/_ref' if kind.startswith('ref') else 'oracle C port'}, -O3 -DNDEBUG, ROS logging compiled out)",
+            "rollouts_per_s": rollouts / max(secs + t_nn, 1e-9)}
+
+
+def work_profile(boxes, tree_records, samples, heur, n=32):
+    """R (reference points scanned per waypoint search) and A (SAT axes per box pair) as the reference executes
+    this workload, counted by the oracle port on a few rollouts (SURVEY.md §8d uses them in the FLOP count)."""
+    from cpulib import CpuPlanner
+    orc = CpuPlanner("oracle")
+    orc.set_obstacles(boxes)
+    orc.tree_init(CAR, GOAL, VMAX)
+    orc.tree_import(tree_records)
+    c0 = (ctypes.c_long * 3)()
+    orc._f("work_counters")(c0)
+    cand, _, cnt = orc.nearest_batch(samples[:n], heur[:n])
+    ok = cnt > 0
+    out = orc.rollout_batch(cand[ok, 0], samples[:n][ok])
+    c1 = (ctypes.c_long * 3)()
+    orc._f("work_counters")(c1)
+    steps = max(1, int(out[:, 14].sum()))
+    sat_calls, sat_axes, scanned = (c1[i] - c0[i] for i in range(3))
+    return scanned / steps, (sat_axes / sat_calls if sat_calls else 1.0)
+
+
+def algorithmic_flop_per_step(n_obs, R=1.0, A=1.17):
+    """F_core 166 + waypoint scan 6R + collision 38 + n_obs (42 + 40 A)."""
+    return 166.0 + 6.0 * R + 38.0 + n_obs * (42.0 + 40.0 * A)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import clrrt_b200 as clrrt
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # a dedicated (non-default) stream shared by torch and the library: torch.cuda.Event then times the library's kernels
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
+    pl = clrrt.Planner(device=local, tree_capacity=TREE_SNAPSHOT + 2 * K_ROUND * world + 1024, max_round=K_ROUND,
+                       stream=stream.cuda_stream)
+    boxes, smp, heu = build_workload(pl, clrrt, rank, world)
+    n0 = pl.tree_size()
+    d_smp = torch.from_numpy(smp).cuda()
+    d_heu = torch.from_numpy(heu).cuda()
+    h_smp = torch.from_numpy(smp).pin_memory()
+    h_heu = torch.from_numpy(heu).pin_memory()
+    if world > 1:
+        pl.set_defer_append(True)
+        rec_bytes = clrrt.RECORD_BYTES
+        max_rec = 2 * K_ROUND
+        gathered = torch.empty(world * max_rec * rec_bytes, dtype=torch.uint8, device="cuda")
+        counts_t = torch.zeros(world, dtype=torch.int32, device="cuda")
+
+    def exchange():
+        """per-round node all-gather over NCCL: per-rank counts, then fixed-stride records; every rank appends all
+        ranks' chunks in rank order (= global sample order), so the trees stay identical."""
+        ptr, n = pl.round_records()
+        mine = torch.tensor([n], dtype=torch.int32, device="cuda")
+        dist.all_gather_into_tensor(counts_t, mine)
+        counts = counts_t.cpu().numpy()
+        m = int(counts.max())
+        if m == 0:
+            return 0
+        src = _as_cuda_tensor(ptr, max_rec * rec_bytes, local)[:m * rec_bytes]
+        dst = gathered[:world * m * rec_bytes]
+        dist.all_gather_into_tensor(dst, src)
+        pl.append_records(dst.data_ptr(), counts, m)
+        return int(counts.sum())
+
+    def one_round(dev_inputs=True):
+        if dev_inputs:
+            st = pl.expand_round_dev(d_smp.data_ptr(), d_heu.data_ptr(), K_ROUND)
+        else:
+            d_smp.copy_(h_smp, non_blocking=True)
+            d_heu.copy_(h_heu, non_blocking=True)
+            st = pl.expand_round_dev(d_smp.data_ptr(), d_heu.data_ptr(), K_ROUND)
+        added = exchange() if world > 1 else st.nodes_added
+        return st, added
+
+    def timed(dev_inputs, steps, download):
+        tot_steps = tot_roll = 0
+        ms_roll = 0.0
+        launches = 0
+        d2h = 0
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            st, added = one_round(dev_inputs)
+            if download:  # the step's result: the accepted node records, back on the host
+                nodes = pl.tree_download_range(n0, pl.tree_size() - n0)
+                d2h = nodes.nbytes + ctypes.sizeof(clrrt.RoundStats)
+            pl.tree_truncate(n0)
+            tot_steps += st.sim_steps
+            tot_roll += st.rollouts
+            ms_roll += st.ms_rollout
+            launches += 7 + (1 if st.ms_goal > 0 else 0)
+        e1.record(stream)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms, float(tot_steps), float(tot_roll)], dtype=torch.float64, device="cuda")
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            ms, tot_steps, tot_roll = float(tmax[0]), int(t[1]), int(t[2])
+        return ms, tot_steps, tot_roll, ms_roll, launches, d2h, st
+
+    for _ in range(args.warmup):
+        one_round(True)
+        pl.tree_truncate(n0)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, tot_steps, tot_roll, ms_roll, launches, _, st = timed(True, args.steps, False)
+    e_ms, e_steps, e_roll, _, _, d2h, _ = timed(False, args.steps, True)
+    sampler.stop_flag = True
+    clocks = sampler.summary() if rank == 0 else None
+    if rank != 0:
+        pl.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = tot_steps / (ms * 1e-3)
+    # roofline of the dominant kernel (rollout_kernel<false>), measured live with the library's CUDA events on the
+    # launch stream: algorithmic FLOP of the steps it executed / its device time, against the FP32 pipe peak at the
+    # SM clock sampled during the run.
+    cpu = None
+    tree_rec = pl.tree_download_records()[:n0]
+    R_A = work_profile(boxes, tree_rec, smp, heu)
+    if not args.no_cpu_baseline:
+        cpu = cpu_baseline_sample(boxes, tree_rec, smp, heu, budget_s=args.cpu_seconds)
+    n_obs = len(boxes)
+    flop_step = algorithmic_flop_per_step(n_obs, *R_A)
+    per_launch_steps = st.sim_steps  # last round, this rank
+    kernel_ms = ms_roll / args.steps
+    achieved = flop_step * per_launch_steps / (kernel_ms * 1e-3) / 1e12
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    props = torch.cuda.get_device_properties(local)
+    peak = props.multi_processor_count * 128 * 2 * sm_mhz * 1e6 / 1e12
+    hbm_bytes = 190.0 * (tot_roll / max(1, args.steps) / world)
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        peaks = {"hbm_gbs": 6650.0}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 rollout + f32 SAT/Dubins (the reference's mixture)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "samples_per_round_per_gpu": K_ROUND, "tree_nodes": n0, "obstacles": n_obs,
+                   "parallelism": f"samples sharded over {world} GPU(s), tree replicated, node all-gather per round" if world > 1 else "1 GPU",
+                   "l2_policy": "per-round inputs+outputs (samples, candidate lists, staging SoA, records: ~40 MB) are rewritten every round; the kernel is compute-bound, no L2 flush needed"},
+        "rollouts_per_s": tot_roll / (ms * 1e-3), "sim_steps_per_round": tot_steps / args.steps,
+        "e2e": {"value": e_steps / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(smp.nbytes + heu.nbytes),
+                "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "fp32-pipe (CUDA cores; no tensor work on this path)", "kernel": "rollout_kernel<false>",
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s (algorithmic, SURVEY.md §8d count)",
+                     "frac": achieved / peak,
+                     "peak_source": f"derived: {props.multi_processor_count} SMs x 128 FP32 lanes x 2 x {sm_mhz:.0f} MHz sampled in-run",
+                     "kernel_ms_per_launch": kernel_ms, "algorithmic_flop_per_sim_step": flop_step,
+                     "reference_work_profile": {"points_scanned_per_step_R": R_A[0], "sat_axes_per_pair_A": R_A[1]},
+                     "traffic": None,
+                     "hbm": {"achieved_gbs": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
+                             "note": "algorithmic ~190 B per rollout; HBM is idle on this path"}},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    pl.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _as_cuda_tensor(ptr, nbytes, device):
+    """Zero-copy torch view of a device buffer owned by the library (for NCCL all-gather)."""
+    import torch
+
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+    return torch.as_tensor(h, device=torch.device("cuda", device))
+
+
+def _ref_worker(args):
+    """One process = one copy of the (single-threaded, global-state) reference on a disjoint shard."""
+    shard, n_per_step, steps, warmup, tree, boxes, samples, heur = args
+    from cpulib import CpuPlanner, ref_available
+    cpu = CpuPlanner("ref_defined" if ref_available(True) else "oracle")
+    cpu.set_obstacles(boxes)
+    cpu.tree_init(CAR, GOAL, VMAX)
+    cpu.tree_import(tree)
+    out = []
+    for s in range(warmup + steps):
+        lo = (shard * (warmup + steps) + s) * n_per_step
+        t0 = time.perf_counter()
+        cand, _, cnt = cpu.nearest_batch(samples[lo:lo + n_per_step], heur[lo:lo + n_per_step])
+        ok = cnt > 0
+        o = cpu.rollout_batch(cand[ok, 0], samples[lo:lo + n_per_step][ok])
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            out.append((dt, int(o[:, 14].sum()), int(ok.sum())))
+    return out
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation (oracle/_ref, else the oracle port) on all host
+    cores, each step a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from cpulib import CpuPlanner, ref_available
+    kind = "ref_defined" if ref_available(True) else "oracle"
+    boxes = scene_c3_boxes()
+    # the same tree snapshot needs the GPU library; without a GPU grow a smaller one with the CPU code itself
+    tree = None
+    try:
+        import torch
+        if torch.cuda.is_available():
+            import clrrt_b200 as clrrt
+            pl = clrrt.Planner(device=0, tree_capacity=TREE_SNAPSHOT + 2 * K_ROUND + 1024, max_round=K_ROUND)
+            build_workload(pl, clrrt, 0, 1)
+            tree = pl.tree_download_records()[:TREE_SNAPSHOT]
+            pl.close()
+    except Exception:
+        tree = None
+    if tree is None:
+        cpu = CpuPlanner(kind)
+        cpu.set_obstacles(boxes)
+        cpu.srand(1)
+        cpu.tree_init(CAR, GOAL, VMAX)
+        cpu.expand(300)
+        tree = cpu.tree_export()
+    import clrrt_b200 as clrrt
+    cores = os.cpu_count() or 1
+    n_per_step = 16
+    samples, heur = clrrt.draw_samples(GOAL, cores * (args.steps + args.warmup) * n_per_step, seed=2)
+    jobs = [(w, n_per_step, args.steps, args.warmup, tree, boxes, samples, heur) for w in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_ref_worker, jobs)
+    wall = time.perf_counter() - t0
+    per_step = [max(r[s][0] for r in res) for s in range(args.steps)]
+    steps_total = sum(x[1] for r in res for x in r)
+    roll_total = sum(x[2] for r in res for x in r)
+    secs = sum(per_step)
+    value = steps_total / secs
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 rollout + f32 SAT/Dubins", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "tree_nodes": int(len(tree)), "obstacles": int(len(boxes))},
+            "rollouts_per_s": roll_total / secs,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference" if kind.startswith("ref") else "port",
+                             "sample": f"each step: {n_per_step} samples per core x {cores} independent single-threaded reference processes "
+                                       f"(candidate search + top-1 rollout), {roll_total} rollouts / {steps_total} sim steps in total, wall {wall:.1f} s"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

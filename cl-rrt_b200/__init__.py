@@ -92,6 +92,9 @@ def load_library():
     lib.clrrt_round_records.argtypes = [vp, C.POINTER(vp), C.POINTER(ip)]
     lib.clrrt_append_records.argtypes = [vp, vp, vp, ip, ip]
     lib.clrrt_set_tuning.argtypes = [vp, ip, ip]
+    lib.clrrt_tree_download_range.argtypes = [vp, ip, ip, vp]
+    lib.clrrt_draw_samples.argtypes = [vp, ip, vp, vp]
+    lib.srand = C.CDLL(None).srand
     _lib = lib
     return lib
 
@@ -100,6 +103,20 @@ def default_params():
     p = Params()
     load_library().clrrt_default_params(C.byref(p))
     return p
+
+
+def draw_samples(goal, K, seed=None):
+    """sampleAroundVehicle + heuristic draw on the C library's rand() (rrt/src/rrtplanner.cpp:133-143, :187-201)."""
+    lib = load_library()
+    if seed is not None:
+        C.CDLL(None).srand(C.c_uint(seed))
+    g = (C.c_double * 4)(*[float(x) for x in goal])
+    s = np.zeros((K, 2))
+    h = np.zeros(K, np.uint8)
+    rc = lib.clrrt_draw_samples(g, K, s.ctypes.data, h.ctypes.data)
+    if rc != 0:
+        raise ClrrtError(f"clrrt_draw_samples failed ({rc})")
+    return s, h
 
 
 def root_node(car_state6):
@@ -212,6 +229,11 @@ class Planner:
         got = C.c_int(0)
         self._ck(self.lib.clrrt_tree_download(self.h, out.ctypes.data, n, C.byref(got)))
         return out[:got.value]
+
+    def tree_download_range(self, first, count):
+        out = np.zeros(count, NODE_DTYPE)
+        self._ck(self.lib.clrrt_tree_download_range(self.h, first, count, out.ctypes.data))
+        return out
 
     def tree_download_records(self):
         t = self.tree_download()

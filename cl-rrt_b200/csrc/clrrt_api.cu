@@ -38,6 +38,7 @@ struct clrrt_ctx {
   NodeSoA tree{}, stage{};
   void *tree_mem = nullptr, *stage_mem = nullptr;
   ObsHot* d_hot = nullptr;
+  ObsBound* d_bnd = nullptr;
   ObsCold* d_cold = nullptr;
   ObsMoving* d_mov = nullptr;
   int obs_cap = 0;
@@ -101,9 +102,9 @@ inline double hmax(double a, double b) { return (a < b) ? b : a; }
 void fill_dev_params(clrrt_ctx* ctx) {
   const clrrt_params& p = ctx->prm;
   DevParams& d = ctx->dprm;
-  const int ns = d.n_static, nm = d.n_moving, sm = d.static_in_smem;
+  const int ns = d.n_static, nm = d.n_moving, sm = d.static_in_smem, nsp = d.n_static_pad;
   memset(&d, 0, sizeof d);
-  d.n_static = ns; d.n_moving = nm; d.static_in_smem = sm;
+  d.n_static = ns; d.n_moving = nm; d.static_in_smem = sm; d.n_static_pad = nsp;
   d.dmax = p.veh.dmax; d.ddmax = p.veh.ddmax; d.inv_Td = 1 / p.veh.Td; d.inv_Ta = 1 / p.veh.Ta;
   d.amin = p.veh.amin; d.amax = p.veh.amax; d.L = p.veh.L; d.Vch = p.veh.Vch; d.Kus = p.veh.Kus;
   d.sim_dt = p.sim_dt; d.mindla = p.ctrl_mindla; d.tla = p.ctrl_tla;
@@ -129,6 +130,8 @@ void fill_dev_params(clrrt_ctx* ctx) {
   // OBB vOBB(vPos, 2, 4.848, theta): float w, h (collision.h:24); setVertices uses w/2, h/2
   const float vw = 2, vh = 4.848;
   d.veh_hw = vw / 2; d.veh_hh = vh / 2;
+  d.veh_reach = std::sqrt(d.veh_hw * d.veh_hw + d.veh_hh * d.veh_hh);
+  d.exact_dist = (p.Wcost[2] != 0.0) ? 1 : 0;  // the distance only enters the cost through W2*exp(-W3*Dobs)
   int ms = 0;
   while (ms < (20 / p.sim_dt) && ms < CLRRT_MAX_STEPS_CAP * 64) ms++;  // simulation.cpp:58
   d.max_steps = ms;
@@ -146,12 +149,20 @@ int ensure_params(clrrt_ctx* ctx) {
 }
 
 int configure_launch(clrrt_ctx* ctx) {
-  ctx->smem_bytes = ctx->dprm.static_in_smem ? (size_t)ctx->dprm.n_static * sizeof(ObsHot) : 0;
-  CK(cudaFuncSetAttribute(rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
-  CK(cudaFuncSetAttribute(rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+  ctx->smem_bytes = ctx->dprm.static_in_smem ? (size_t)ctx->dprm.n_static * sizeof(ObsHot) + (size_t)ctx->dprm.n_static_pad * sizeof(ObsBound) : 0;
+  const int sm = (int)ctx->smem_bytes;
+  CK(cudaFuncSetAttribute(rollout_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(rollout_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(rollout_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(rollout_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   int b0 = 1, b1 = 1;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rollout_kernel<false>, ROLLOUT_THREADS, ctx->smem_bytes));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, rollout_kernel<true>, ROLLOUT_THREADS, ctx->smem_bytes));
+  if (ctx->dprm.exact_dist) {
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rollout_kernel<false, true>, ROLLOUT_THREADS, ctx->smem_bytes));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, rollout_kernel<true, true>, ROLLOUT_THREADS, ctx->smem_bytes));
+  } else {
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rollout_kernel<false, false>, ROLLOUT_THREADS, ctx->smem_bytes));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, rollout_kernel<true, false>, ROLLOUT_THREADS, ctx->smem_bytes));
+  }
   ctx->blocks_per_sm_main = std::max(1, b0);
   ctx->blocks_per_sm_gb = std::max(1, b1);
   return CLRRT_OK;
@@ -164,7 +175,10 @@ template <bool GB> int launch_rollout(clrrt_ctx* ctx, const RolloutJob& job, int
   int blocks = ctx->num_sms * per_sm;  // persistent grid: a multiple of the SM count
   const int needed = (n_items_hint + lanes_per_block - 1) / lanes_per_block;
   if (needed < blocks) blocks = std::max(1, needed);
-  rollout_kernel<GB><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_hot, ctx->d_cold, ctx->d_mov);
+  if (ctx->dprm.exact_dist)
+    rollout_kernel<GB, true><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov);
+  else
+    rollout_kernel<GB, false><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov);
   CK(cudaGetLastError());
   return CLRRT_OK;
 }
@@ -251,7 +265,7 @@ int clrrt_destroy(clrrt_ctx* ctx) {
   if (!ctx) return CLRRT_ERR_ARG;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  void* ptrs[] = {ctx->tree_mem, ctx->stage_mem, ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_samples, ctx->d_heur,
+  void* ptrs[] = {ctx->tree_mem, ctx->stage_mem, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_samples, ctx->d_heur,
                   ctx->d_cand, ctx->d_key, ctx->d_count, ctx->d_valid, ctx->d_gb_list, ctx->d_ints, ctx->d_block_sums,
                   ctx->d_records, ctx->d_counters, ctx->batch.d_parent, ctx->batch.d_list0, ctx->batch.d_list1,
                   ctx->batch.d_samples, ctx->batch.d_out, ctx->batch.d_traj};
@@ -280,6 +294,9 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
   if (!ctx || n < 0 || (n > 0 && !host)) return CLRRT_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   std::vector<ObsHot> hot;
+  std::vector<ObsBound> bnd;
+  const float margin = 0.1f;  // see rollout.cuh: circles farther apart than this cannot collide in the reference's SAT
+  const float vreach = ctx->dprm.veh_reach;
   std::vector<ObsCold> cold;
   std::vector<ObsMoving> mov;
   for (int i = 0; i < n; i++) {
@@ -312,18 +329,27 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
       }
       hot.push_back(a);
       cold.push_back(c);
+      const float reach = std::sqrt((h / 2) * (h / 2) + (w / 2) * (w / 2)) + vreach + margin;
+      ObsBound b; b.cx = (float)o.cx; b.cy = (float)o.cy; b.R2 = reach * reach; b.vxy_unused = 0;
+      bnd.push_back(b);
     } else {
       ObsMoving m;
       m.cx = o.cx; m.cy = o.cy; m.vx = o.vx; m.vy = o.vy; m.ch = ch; m.sw = sw; m.sh = sh; m.cw = cw;
+      const float reach = std::sqrt((h / 2) * (h / 2) + (w / 2) * (w / 2)) + vreach + margin + 0.05f;  // + float centre prediction slack
+      m.R2 = reach * reach; m.pad[0] = m.pad[1] = m.pad[2] = 0;
       mov.push_back(m);
     }
   }
-  const int total = std::max<int>(1, n);
+  while (bnd.size() % 8) { ObsBound b; b.cx = 0; b.cy = 0; b.R2 = -1.0f; b.vxy_unused = 0; bnd.push_back(b); }
+  if (hot.size() + mov.size() > 65000) { ctx->err = "more than 65000 obstacles"; return CLRRT_ERR_CAPACITY; }
+  const int total = std::max<int>(8, n + 8);
   if (total > ctx->obs_cap) {
     if (ctx->d_hot) cudaFree(ctx->d_hot);
+    if (ctx->d_bnd) cudaFree(ctx->d_bnd);
     if (ctx->d_cold) cudaFree(ctx->d_cold);
     if (ctx->d_mov) cudaFree(ctx->d_mov);
-    ctx->d_hot = nullptr; ctx->d_cold = nullptr; ctx->d_mov = nullptr;
+    ctx->d_hot = nullptr; ctx->d_cold = nullptr; ctx->d_mov = nullptr; ctx->d_bnd = nullptr;
+    CK(cudaMalloc((void**)&ctx->d_bnd, total * sizeof(ObsBound)));
     CK(cudaMalloc((void**)&ctx->d_hot, total * sizeof(ObsHot)));
     CK(cudaMalloc((void**)&ctx->d_cold, total * sizeof(ObsCold)));
     CK(cudaMalloc((void**)&ctx->d_mov, total * sizeof(ObsMoving)));
@@ -333,12 +359,14 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
   if (!hot.empty()) {
     CK(cudaMemcpy(ctx->d_hot, hot.data(), hot.size() * sizeof(ObsHot), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_cold, cold.data(), cold.size() * sizeof(ObsCold), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_bnd, bnd.data(), bnd.size() * sizeof(ObsBound), cudaMemcpyHostToDevice));
   }
   if (!mov.empty()) CK(cudaMemcpy(ctx->d_mov, mov.data(), mov.size() * sizeof(ObsMoving), cudaMemcpyHostToDevice));
   ctx->dprm.n_static = (int)hot.size();
   ctx->dprm.n_moving = (int)mov.size();
+  ctx->dprm.n_static_pad = (int)bnd.size();
   // the hot table (32 B per obstacle) is staged in shared memory when it fits next to a second resident block
-  ctx->dprm.static_in_smem = (hot.size() * sizeof(ObsHot) <= 96 * 1024) ? 1 : 0;
+  ctx->dprm.static_in_smem = (hot.size() * sizeof(ObsHot) + bnd.size() * sizeof(ObsBound) <= 96 * 1024) ? 1 : 0;
   int rc = configure_launch(ctx);
   if (rc != CLRRT_OK) return rc;
   return upload_params(ctx);
@@ -380,25 +408,24 @@ int clrrt_tree_truncate(clrrt_ctx* ctx, int n) {
   return CLRRT_OK;
 }
 
-int clrrt_tree_download(clrrt_ctx* ctx, clrrt_node* host, int cap, int* n_out) {
-  if (!ctx || !host || cap < 0) return CLRRT_ERR_ARG;
+int clrrt_tree_download_range(clrrt_ctx* ctx, int first, int n, clrrt_node* host) {
+  if (!ctx || !host || first < 0 || n < 0 || first + n > ctx->n_tree) return CLRRT_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  const int n = std::min(cap, ctx->n_tree);
-  if (n_out) *n_out = n;
   if (n == 0) return CLRRT_OK;
   std::vector<double> d((size_t)n * 15);
   std::vector<float> f((size_t)n * 2);
   std::vector<int32_t> q((size_t)n * 3);
-  CK(cudaStreamSynchronize(ctx->stream));
   const double* dsrc[15] = {ctx->tree.x, ctx->tree.y, ctx->tree.th, ctx->tree.de, ctx->tree.v, ctx->tree.a, ctx->tree.t,
                             ctx->tree.s7, ctx->tree.s8, ctx->tree.s9, ctx->tree.rfx, ctx->tree.rfy, ctx->tree.rbx,
                             ctx->tree.rby, ctx->tree.vback};
-  for (int k = 0; k < 15; k++) CK(cudaMemcpy(d.data() + (size_t)k * n, dsrc[k], (size_t)n * 8, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(f.data(), ctx->tree.costE, (size_t)n * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(f.data() + n, ctx->tree.costS, (size_t)n * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(q.data(), ctx->tree.parent, (size_t)n * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(q.data() + n, ctx->tree.goal, (size_t)n * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(q.data() + 2 * (size_t)n, ctx->tree.nref, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  cudaStream_t st = ctx->stream;
+  for (int k = 0; k < 15; k++) CK(cudaMemcpyAsync(d.data() + (size_t)k * n, dsrc[k] + first, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(f.data(), ctx->tree.costE + first, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(f.data() + n, ctx->tree.costS + first, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(q.data(), ctx->tree.parent + first, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(q.data() + n, ctx->tree.goal + first, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(q.data() + 2 * (size_t)n, ctx->tree.nref + first, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   for (int i = 0; i < n; i++) {
     clrrt_node& o = host[i];
     for (int k = 0; k < 10; k++) o.state[k] = d[(size_t)k * n + i];
@@ -407,6 +434,32 @@ int clrrt_tree_download(clrrt_ctx* ctx, clrrt_node* host, int cap, int* n_out) {
     o.ref_vback = d[(size_t)14 * n + i];
     o.costE = f[i]; o.costS = f[(size_t)n + i];
     o.parent = q[i]; o.goal_reached = q[(size_t)n + i]; o.n_ref = q[2 * (size_t)n + i]; o.reserved = 0;
+  }
+  return CLRRT_OK;
+}
+
+int clrrt_tree_download(clrrt_ctx* ctx, clrrt_node* host, int cap, int* n_out) {
+  if (!ctx || !host || cap < 0) return CLRRT_ERR_ARG;
+  const int n = std::min(cap, ctx->n_tree);
+  if (n_out) *n_out = n;
+  return clrrt_tree_download_range(ctx, 0, n, host);
+}
+
+int clrrt_draw_samples(const double goal[4], int K, double* sample_xy, uint8_t* heuristic) {
+  if (!goal || !sample_xy || !heuristic || K < 0) return CLRRT_ERR_ARG;
+  const double pi = M_PI;
+  for (int j = 0; j < K; j++) {
+    // sampleAroundVehicle, rrtplanner.cpp:187-201
+    const double dGoal = sqrt(goal[0] * goal[0] + goal[1] * goal[1]);
+    const double goalHeading = atan2(goal[1], goal[0]);
+    const double latMin = -7, latMax = 7;
+    const double rLong = static_cast<float>(rand()) / (static_cast<float>(RAND_MAX / (dGoal + 10)));
+    const double rLat = latMin + static_cast<float>(rand()) / (static_cast<float>(RAND_MAX / (latMax - latMin)));
+    sample_xy[2 * j] = rLong * cos(goalHeading) + rLat * cos(goalHeading + pi / 2);
+    sample_xy[2 * j + 1] = rLong * sin(goalHeading) + rLat * sin(goalHeading + pi / 2);
+    // heuristic draw, rrtplanner.cpp:142-143 (RRT.goalReached is never set: threshold stays 0.7)
+    const double r = static_cast<double>(rand()) / (static_cast<double>(RAND_MAX / (1)));
+    heuristic[j] = (r <= 0.7) ? 0 : 1;
   }
   return CLRRT_OK;
 }

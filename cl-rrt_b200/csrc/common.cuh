@@ -50,11 +50,16 @@ struct __align__(16) ObsCold {  // read only when the vehicle's own axes did not
   float nx[4], ny[4];           // axes; ny[3] = 0 (never written upstream, "defined" variant)
   float pmax[4], pmin[4];       // the obstacle's own projection interval on each of its axes
 };
+// Broad-phase record (verdict-only mode, see rollout.cuh): centre and squared reach of the bounding circle.
+struct __align__(16) ObsBound {
+  float cx, cy, R2, vxy_unused;  // R2 = (half diagonal + vehicle half diagonal + margin)^2
+};
 // Moving obstacles: centre = c + vel*t with t = x[6] of the lane, so vertices are rebuilt per step from
 // host-computed float half-extent products (the float operation order of setVertices is preserved).
 struct __align__(16) ObsMoving {
   double cx, cy, vx, vy;
   float ch, sw, sh, cw;  // cosf(o)*(h/2), sinf(o)*(w/2), sinf(o)*(h/2), cosf(o)*(w/2)
+  float R2, pad[3];      // broad phase: (half diagonal + vehicle half diagonal + margin)^2
 };
 
 // ---- parameters in constant memory -----------------------------------------------------------------------
@@ -74,7 +79,10 @@ struct DevParams {
   int32_t max_steps;     // number of i with i < 20/sim_dt, rrt/src/simulation.cpp:58
   int32_t obs_use_pred;
   int32_t n_static, n_moving;
+  int32_t n_static_pad;  // n_static rounded up to a multiple of 8 (broad-phase table is padded with never-near entries)
   int32_t static_in_smem;
+  int32_t exact_dist;    // 1: return the reference's pseudo-distance (needed when W[2] != 0); 0: verdict only
+  float veh_reach;       // half diagonal of the vehicle box (broad phase)
 };
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }

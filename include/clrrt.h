@@ -129,6 +129,7 @@ int clrrt_tree_reset(clrrt_ctx* ctx, const clrrt_node* host, int n);
 int clrrt_tree_size(const clrrt_ctx* ctx);
 int clrrt_tree_truncate(clrrt_ctx* ctx, int n); /* drop nodes >= n (bench: same snapshot every round) */
 int clrrt_tree_download(clrrt_ctx* ctx, clrrt_node* host, int cap, int* n);
+int clrrt_tree_download_range(clrrt_ctx* ctx, int first, int count, clrrt_node* host);
 
 /* == sortNodesExplore (heuristic[j]==0) / sortNodesOptimize (==1), rrt/src/rrtplanner.cpp:227-268, for K samples
  * against the current tree: up to CLRRT_SORT_LIMIT feasible node ids in increasing key order (ties: lower id),
@@ -156,6 +157,11 @@ int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint
 int clrrt_best_path(clrrt_ctx* ctx, int32_t* ids, int cap, int* n);
 
 int clrrt_counters_get(clrrt_ctx* ctx, clrrt_counters* out);
+
+/* == sampleAroundVehicle (rrt/src/rrtplanner.cpp:187-201) + the heuristic draw (:142-143), K times, on the host
+ * C library's rand() (the reference never seeds it: srand(1) stream; the caller may srand()).  Three draws per
+ * sample in the reference's order: longitudinal, lateral, heuristic.  heuristic[j] = 0 explore (r <= 0.7), 1 optimize. */
+int clrrt_draw_samples(const double goal[4], int K, double* sample_xy, uint8_t* heuristic);
 
 /* Multi-GPU (one context per rank): after a round run with append deferred, the nodes accepted by this rank are
  * exposed as fixed-stride records for an all-gather (NCCL), and the gathered records of all ranks are appended
