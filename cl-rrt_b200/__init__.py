@@ -46,7 +46,7 @@ class Counters(C.Structure):
 # numpy views of the C structs clrrt_node / clrrt_rollout / clrrt_obstacle
 NODE_DTYPE = np.dtype([("state", "f8", 10), ("ref_front", "f8", 2), ("ref_back", "f8", 2), ("ref_vback", "f8"),
                        ("costE", "f4"), ("costS", "f4"), ("parent", "i4"), ("goal_reached", "i4"), ("n_ref", "i4"),
-                       ("reserved", "i4")], align=True)
+                       ("kind", "i4"), ("sample", "f8", 2)], align=True)
 ROLLOUT_DTYPE = np.dtype([("state", "f8", 10), ("costE", "f8"), ("costS", "f8"), ("ref_back", "f8", 2),
                           ("ref_vback", "f8"), ("trace", "f8"), ("end_reached", "i4"), ("goal_reached", "i4"),
                           ("n_steps", "i4"), ("fail", "i4"), ("n_ref", "i4"), ("idwp0", "i4"), ("tainted", "i4"),
@@ -84,6 +84,7 @@ def load_library():
     lib.clrrt_tree_download.argtypes = [vp, vp, ip, C.POINTER(ip)]
     lib.clrrt_nearest_batch.argtypes = [vp, vp, vp, ip, vp, vp, vp]
     lib.clrrt_propagate_batch.argtypes = [vp, vp, vp, vp, ip, vp, vp, ip]
+    lib.clrrt_propagate_batch_ex.argtypes = [vp, vp, vp, vp, ip, vp, vp, ip, vp, ip]
     lib.clrrt_expand_round.argtypes = [vp, vp, vp, ip, C.POINTER(RoundStats)]
     lib.clrrt_expand_round_dev.argtypes = [vp, vp, vp, ip, C.POINTER(RoundStats)]
     lib.clrrt_best_path.argtypes = [vp, vp, ip, C.POINTER(ip)]
@@ -261,16 +262,20 @@ class Planner:
                                               key.ctypes.data, cnt.ctypes.data))
         return cand, key, cnt
 
-    def propagate_batch(self, parent, samples, goal_biased=None, traj_stride=0):
+    def propagate_batch(self, parent, samples, goal_biased=None, traj_stride=0, ref_stride=0):
         par = np.ascontiguousarray(parent, dtype=np.int32)
         s = np.ascontiguousarray(samples, dtype=np.float64).reshape(-1, 2)
         M = len(par)
         gb = None if goal_biased is None else np.ascontiguousarray(goal_biased, dtype=np.uint8)
         out = np.zeros(M, ROLLOUT_DTYPE)
         traj = np.zeros((M, traj_stride, 10)) if traj_stride else None
-        self._ck(self.lib.clrrt_propagate_batch(self.h, par.ctypes.data, s.ctypes.data,
-                                                None if gb is None else gb.ctypes.data, M, out.ctypes.data,
-                                                None if traj is None else traj.ctypes.data, traj_stride))
+        ref = np.zeros((M, ref_stride, 3)) if ref_stride else None
+        self._ck(self.lib.clrrt_propagate_batch_ex(self.h, par.ctypes.data, s.ctypes.data,
+                                                   None if gb is None else gb.ctypes.data, M, out.ctypes.data,
+                                                   None if traj is None else traj.ctypes.data, traj_stride,
+                                                   None if ref is None else ref.ctypes.data, ref_stride))
+        if ref_stride:
+            return out, traj, ref
         return (out, traj) if traj_stride else out
 
     def expand_round(self, samples, heuristic):

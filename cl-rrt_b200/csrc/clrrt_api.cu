@@ -24,6 +24,8 @@ struct RolloutScratch {
   clrrt_rollout* d_out = nullptr;
   double* d_traj = nullptr;
   size_t traj_cap = 0;
+  double* d_ref = nullptr;
+  size_t ref_cap = 0;
 };
 
 }  // namespace
@@ -39,6 +41,7 @@ struct clrrt_ctx {
   void *tree_mem = nullptr, *stage_mem = nullptr;
   ObsHot* d_hot = nullptr;
   ObsBound* d_bnd = nullptr;
+  ObsBound* d_grp = nullptr;
   ObsCold* d_cold = nullptr;
   ObsMoving* d_mov = nullptr;
   int obs_cap = 0;
@@ -46,6 +49,9 @@ struct clrrt_ctx {
   double* d_samples = nullptr;
   uint8_t* d_heur = nullptr;
   int32_t *d_cand = nullptr, *d_count = nullptr, *d_valid = nullptr, *d_gb_list = nullptr;
+  int32_t *d_best = nullptr, *d_slot = nullptr;
+  uint8_t* d_res_code = nullptr;
+  uint16_t* d_res_steps = nullptr;
   float* d_key = nullptr;
   int32_t* d_ints = nullptr;  // [0] head main, [1] head gb, [2] gb_count, [3] total records, [4] best id
   int32_t* d_block_sums = nullptr;
@@ -85,15 +91,19 @@ int alloc_soa(clrrt_ctx* ctx, NodeSoA& s, void** mem, int n) {
   CK(cudaMalloc(mem, bytes));
   CK(cudaMemsetAsync(*mem, 0, bytes, ctx->stream));
   double* d = reinterpret_cast<double*>(*mem);
-  double** df[] = {&s.x, &s.y, &s.th, &s.de, &s.v, &s.a, &s.t, &s.s7, &s.s8, &s.s9, &s.rfx, &s.rfy, &s.rbx, &s.rby, &s.vback, &s.angPar};
+  double** df[] = {&s.x, &s.y, &s.th, &s.de, &s.v, &s.a, &s.t, &s.s7, &s.s8, &s.s9, &s.rfx, &s.rfy, &s.rbx, &s.rby, &s.vback, &s.angPar, &s.smx, &s.smy};
   for (size_t i = 0; i < nd; i++) *df[i] = d + i * n8;
   float* f = reinterpret_cast<float*>(d + nd * n8);
   float** ff[] = {&s.costE, &s.costS, &s.ca, &s.sa};
   for (size_t i = 0; i < nf; i++) *ff[i] = f + i * n8;
   int32_t* q = reinterpret_cast<int32_t*>(f + nf * n8);
-  int32_t** qf[] = {&s.parent, &s.goal, &s.nref};
+  int32_t** qf[] = {&s.parent, &s.goal, &s.nref, &s.kind};
   for (size_t i = 0; i < ni; i++) *qf[i] = q + i * n8;
   return CLRRT_OK;
+}
+
+size_t obstacle_table_bytes(int n_static, int n_groups, int n_groups_pad) {
+  return (size_t)n_static * sizeof(ObsHot) + ((size_t)n_groups * 32 + (size_t)n_groups_pad) * sizeof(ObsBound);
 }
 
 // host-side mirror of std::max semantics used by the reference's lookahead formulas
@@ -102,9 +112,9 @@ inline double hmax(double a, double b) { return (a < b) ? b : a; }
 void fill_dev_params(clrrt_ctx* ctx) {
   const clrrt_params& p = ctx->prm;
   DevParams& d = ctx->dprm;
-  const int ns = d.n_static, nm = d.n_moving, sm = d.static_in_smem, nsp = d.n_static_pad;
+  const int ns = d.n_static, nm = d.n_moving, sm = d.static_in_smem, ng = d.n_groups, ngp = d.n_groups_pad;
   memset(&d, 0, sizeof d);
-  d.n_static = ns; d.n_moving = nm; d.static_in_smem = sm; d.n_static_pad = nsp;
+  d.n_static = ns; d.n_moving = nm; d.static_in_smem = sm; d.n_groups = ng; d.n_groups_pad = ngp;
   d.dmax = p.veh.dmax; d.ddmax = p.veh.ddmax; d.inv_Td = 1 / p.veh.Td; d.inv_Ta = 1 / p.veh.Ta;
   d.amin = p.veh.amin; d.amax = p.veh.amax; d.L = p.veh.L; d.Vch = p.veh.Vch; d.Kus = p.veh.Kus;
   d.sim_dt = p.sim_dt; d.mindla = p.ctrl_mindla; d.tla = p.ctrl_tla;
@@ -149,7 +159,7 @@ int ensure_params(clrrt_ctx* ctx) {
 }
 
 int configure_launch(clrrt_ctx* ctx) {
-  ctx->smem_bytes = ctx->dprm.static_in_smem ? (size_t)ctx->dprm.n_static * sizeof(ObsHot) + (size_t)ctx->dprm.n_static_pad * sizeof(ObsBound) : 0;
+  ctx->smem_bytes = ctx->dprm.static_in_smem ? obstacle_table_bytes(ctx->dprm.n_static, ctx->dprm.n_groups, ctx->dprm.n_groups_pad) : 0;
   const int sm = (int)ctx->smem_bytes;
   CK(cudaFuncSetAttribute(rollout_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   CK(cudaFuncSetAttribute(rollout_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
@@ -176,9 +186,9 @@ template <bool GB> int launch_rollout(clrrt_ctx* ctx, const RolloutJob& job, int
   const int needed = (n_items_hint + lanes_per_block - 1) / lanes_per_block;
   if (needed < blocks) blocks = std::max(1, needed);
   if (ctx->dprm.exact_dist)
-    rollout_kernel<GB, true><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov);
+    rollout_kernel<GB, true><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_grp, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov);
   else
-    rollout_kernel<GB, false><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov);
+    rollout_kernel<GB, false><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_grp, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov);
   CK(cudaGetLastError());
   return CLRRT_OK;
 }
@@ -232,7 +242,7 @@ int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_r
   }
   int rc;
   if ((rc = alloc_soa(ctx, ctx->tree, &ctx->tree_mem, tree_capacity)) != CLRRT_OK) return fail(rc);
-  if ((rc = alloc_soa(ctx, ctx->stage, &ctx->stage_mem, 2 * max_round)) != CLRRT_OK) return fail(rc);
+  if ((rc = alloc_soa(ctx, ctx->stage, &ctx->stage_mem, (CLRRT_SORT_LIMIT + 1) * max_round)) != CLRRT_OK) return fail(rc);
   auto mal = [&](void** ptr, size_t bytes) { return cudaMalloc(ptr, bytes) == cudaSuccess; };
   const size_t K = (size_t)max_round;
   bool ok = true;
@@ -243,6 +253,10 @@ int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_r
   ok &= mal((void**)&ctx->d_count, K * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_valid, 2 * K * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_gb_list, K * sizeof(int32_t));
+  ok &= mal((void**)&ctx->d_best, K * sizeof(int32_t));
+  ok &= mal((void**)&ctx->d_slot, K * sizeof(int32_t));
+  ok &= mal((void**)&ctx->d_res_code, K * CLRRT_SORT_LIMIT);
+  ok &= mal((void**)&ctx->d_res_steps, K * CLRRT_SORT_LIMIT * sizeof(uint16_t));
   ok &= mal((void**)&ctx->d_ints, 16 * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_block_sums, ((K + SCAN_THREADS - 1) / SCAN_THREADS + 1) * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_records, 2 * K * sizeof(NodeRecord));
@@ -265,10 +279,10 @@ int clrrt_destroy(clrrt_ctx* ctx) {
   if (!ctx) return CLRRT_ERR_ARG;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  void* ptrs[] = {ctx->tree_mem, ctx->stage_mem, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_samples, ctx->d_heur,
+  void* ptrs[] = {ctx->tree_mem, ctx->stage_mem, ctx->d_grp, ctx->d_bnd, ctx->d_hot, ctx->d_best, ctx->d_res_code, ctx->d_res_steps, ctx->d_slot, ctx->d_cold, ctx->d_mov, ctx->d_samples, ctx->d_heur,
                   ctx->d_cand, ctx->d_key, ctx->d_count, ctx->d_valid, ctx->d_gb_list, ctx->d_ints, ctx->d_block_sums,
                   ctx->d_records, ctx->d_counters, ctx->batch.d_parent, ctx->batch.d_list0, ctx->batch.d_list1,
-                  ctx->batch.d_samples, ctx->batch.d_out, ctx->batch.d_traj};
+                  ctx->batch.d_samples, ctx->batch.d_out, ctx->batch.d_traj, ctx->batch.d_ref};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->h_ints) cudaFreeHost(ctx->h_ints);
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -293,21 +307,22 @@ int clrrt_set_params(clrrt_ctx* ctx, const clrrt_params* p) {
 int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
   if (!ctx || n < 0 || (n > 0 && !host)) return CLRRT_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  std::vector<ObsHot> hot;
-  std::vector<ObsBound> bnd;
-  const float margin = 0.1f;  // see rollout.cuh: circles farther apart than this cannot collide in the reference's SAT
-  const float vreach = ctx->dprm.veh_reach;
-  std::vector<ObsCold> cold;
+  struct StaticObs { ObsHot hot; ObsCold cold; float cx, cy, reach; uint32_t key; };
+  std::vector<StaticObs> st;
   std::vector<ObsMoving> mov;
+  const float margin = 0.1f;  // rollout.cuh: circles farther apart than this cannot collide in the reference's SAT
+  const float vreach = ctx->dprm.veh_reach;
   for (int i = 0; i < n; i++) {
     const clrrt_obstacle& o = host[i];
     // getOBBvector, old_collisioncheck.cpp:14-16: OBB(centre, size_x/2, size_y/2, theta) with float w, h, o
     const float w = (float)(o.size_x / 2), h = (float)(o.size_y / 2), th = (float)o.theta;
     const float co = cosf(th), so = sinf(th);  // the host libm: bit-identical to the reference's own calls
     const float ch = co * (h / 2), sw = so * (w / 2), sh = so * (h / 2), cw = co * (w / 2);
+    const float reach = std::sqrt((h / 2) * (h / 2) + (w / 2) * (w / 2));
     if (o.vx == 0.0 && o.vy == 0.0) {
-      ObsHot a;
-      ObsCold c;
+      StaticObs s;
+      ObsHot& a = s.hot;
+      ObsCold& c = s.cold;
       const double px = o.cx, py = o.cy;  // centre + 0*t
       a.vx[0] = (float)((px + (double)ch) - (double)sw); a.vy[0] = (float)((py + (double)sh) + (double)cw);
       a.vx[1] = (float)((px + (double)ch) + (double)sw); a.vy[1] = (float)((py + (double)sh) - (double)cw);
@@ -327,46 +342,76 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
         }
         c.pmax[k] = mx; c.pmin[k] = mn;
       }
-      hot.push_back(a);
-      cold.push_back(c);
-      const float reach = std::sqrt((h / 2) * (h / 2) + (w / 2) * (w / 2)) + vreach + margin;
-      ObsBound b; b.cx = (float)o.cx; b.cy = (float)o.cy; b.R2 = reach * reach; b.vxy_unused = 0;
-      bnd.push_back(b);
+      s.cx = (float)o.cx; s.cy = (float)o.cy; s.reach = reach; s.key = 0;
+      st.push_back(s);
     } else {
       ObsMoving m;
       m.cx = o.cx; m.cy = o.cy; m.vx = o.vx; m.vy = o.vy; m.ch = ch; m.sw = sw; m.sh = sh; m.cw = cw;
-      const float reach = std::sqrt((h / 2) * (h / 2) + (w / 2) * (w / 2)) + vreach + margin + 0.05f;  // + float centre prediction slack
-      m.R2 = reach * reach; m.pad[0] = m.pad[1] = m.pad[2] = 0;
+      const float r = reach + vreach + margin + 0.05f;  // + slack for the float centre prediction
+      m.R2 = r * r; m.pad[0] = m.pad[1] = m.pad[2] = 0;
       mov.push_back(m);
     }
   }
-  while (bnd.size() % 8) { ObsBound b; b.cx = 0; b.cy = 0; b.R2 = -1.0f; b.vxy_unused = 0; bnd.push_back(b); }
-  if (hot.size() + mov.size() > 65000) { ctx->err = "more than 65000 obstacles"; return CLRRT_ERR_CAPACITY; }
-  const int total = std::max<int>(8, n + 8);
+  if (st.size() > 32000 || mov.size() > 32000) { ctx->err = "more than 32000 static or moving obstacles"; return CLRRT_ERR_CAPACITY; }
+  // Z-order sort of the static obstacles so that 32 consecutive ones form a compact group (the verdict does not
+  // depend on the order in which obstacles are tested; neither does the minimum distance of the exact mode)
+  if (!st.empty()) {
+    float x0 = st[0].cx, x1 = st[0].cx, y0 = st[0].cy, y1 = st[0].cy;
+    for (auto& s : st) { x0 = std::min(x0, s.cx); x1 = std::max(x1, s.cx); y0 = std::min(y0, s.cy); y1 = std::max(y1, s.cy); }
+    const float ext = std::max(std::max(x1 - x0, y1 - y0), 1e-3f);
+    auto spread = [](uint32_t v) { v &= 0xffff; v = (v | (v << 8)) & 0x00ff00ff; v = (v | (v << 4)) & 0x0f0f0f0f; v = (v | (v << 2)) & 0x33333333; v = (v | (v << 1)) & 0x55555555; return v; };
+    for (auto& s : st) {
+      const uint32_t qx = (uint32_t)(65535.0f * (s.cx - x0) / ext), qy = (uint32_t)(65535.0f * (s.cy - y0) / ext);
+      s.key = spread(qx) | (spread(qy) << 1);
+    }
+    std::stable_sort(st.begin(), st.end(), [](const StaticObs& a, const StaticObs& b) { return a.key < b.key; });
+  }
+  const int ns = (int)st.size();
+  const int ng = (ns + 31) / 32, ngp = std::max(32, ((ng + 31) / 32) * 32);
+  std::vector<ObsHot> hot((size_t)std::max(ns, 1));
+  std::vector<ObsCold> cold((size_t)std::max(ns, 1));
+  std::vector<ObsBound> bnd((size_t)std::max(ng, 1) * 32), grp((size_t)ngp);
+  for (auto& b : bnd) { b.cx = 0; b.cy = 0; b.R2 = -1.0f; b.vxy_unused = 0; }
+  for (auto& g : grp) { g.cx = 0; g.cy = 0; g.R2 = -1.0f; g.vxy_unused = 0; }
+  for (int i = 0; i < ns; i++) {
+    hot[i] = st[i].hot; cold[i] = st[i].cold;
+    const float r = st[i].reach + vreach + margin;
+    bnd[i].cx = st[i].cx; bnd[i].cy = st[i].cy; bnd[i].R2 = r * r;
+  }
+  for (int g = 0; g < ng; g++) {
+    const int lo = g * 32, hi = std::min(ns, lo + 32);
+    double sx = 0, sy = 0;
+    for (int i = lo; i < hi; i++) { sx += st[i].cx; sy += st[i].cy; }
+    const float gx = (float)(sx / (hi - lo)), gy = (float)(sy / (hi - lo));
+    float R = 0;
+    for (int i = lo; i < hi; i++) R = std::max(R, std::sqrt((st[i].cx - gx) * (st[i].cx - gx) + (st[i].cy - gy) * (st[i].cy - gy)) + st[i].reach);
+    const float r = R + vreach + margin + 0.01f;
+    grp[g].cx = gx; grp[g].cy = gy; grp[g].R2 = r * r;
+  }
+  const int total = std::max<int>(32, n + 32);
   if (total > ctx->obs_cap) {
-    if (ctx->d_hot) cudaFree(ctx->d_hot);
-    if (ctx->d_bnd) cudaFree(ctx->d_bnd);
-    if (ctx->d_cold) cudaFree(ctx->d_cold);
-    if (ctx->d_mov) cudaFree(ctx->d_mov);
-    ctx->d_hot = nullptr; ctx->d_cold = nullptr; ctx->d_mov = nullptr; ctx->d_bnd = nullptr;
-    CK(cudaMalloc((void**)&ctx->d_bnd, total * sizeof(ObsBound)));
+    void* old[] = {ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_bnd, ctx->d_grp};
+    for (void* q : old) if (q) cudaFree(q);
+    ctx->d_hot = nullptr; ctx->d_cold = nullptr; ctx->d_mov = nullptr; ctx->d_bnd = nullptr; ctx->d_grp = nullptr;
     CK(cudaMalloc((void**)&ctx->d_hot, total * sizeof(ObsHot)));
     CK(cudaMalloc((void**)&ctx->d_cold, total * sizeof(ObsCold)));
     CK(cudaMalloc((void**)&ctx->d_mov, total * sizeof(ObsMoving)));
+    CK(cudaMalloc((void**)&ctx->d_bnd, (size_t)(total + 32) * sizeof(ObsBound)));
+    CK(cudaMalloc((void**)&ctx->d_grp, (size_t)(((total + 31) / 32 + 31) / 32 * 32 + 32) * sizeof(ObsBound)));
     ctx->obs_cap = total;
   }
   CK(cudaStreamSynchronize(ctx->stream));
-  if (!hot.empty()) {
-    CK(cudaMemcpy(ctx->d_hot, hot.data(), hot.size() * sizeof(ObsHot), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_cold, cold.data(), cold.size() * sizeof(ObsCold), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_bnd, bnd.data(), bnd.size() * sizeof(ObsBound), cudaMemcpyHostToDevice));
-  }
+  CK(cudaMemcpy(ctx->d_hot, hot.data(), hot.size() * sizeof(ObsHot), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_cold, cold.data(), cold.size() * sizeof(ObsCold), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_bnd, bnd.data(), bnd.size() * sizeof(ObsBound), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_grp, grp.data(), grp.size() * sizeof(ObsBound), cudaMemcpyHostToDevice));
   if (!mov.empty()) CK(cudaMemcpy(ctx->d_mov, mov.data(), mov.size() * sizeof(ObsMoving), cudaMemcpyHostToDevice));
-  ctx->dprm.n_static = (int)hot.size();
+  ctx->dprm.n_static = ns;
   ctx->dprm.n_moving = (int)mov.size();
-  ctx->dprm.n_static_pad = (int)bnd.size();
-  // the hot table (32 B per obstacle) is staged in shared memory when it fits next to a second resident block
-  ctx->dprm.static_in_smem = (hot.size() * sizeof(ObsHot) + bnd.size() * sizeof(ObsBound) <= 96 * 1024) ? 1 : 0;
+  ctx->dprm.n_groups = ng;
+  ctx->dprm.n_groups_pad = ngp;
+  // bounds + vertices are staged in shared memory when they leave room for a second resident block
+  ctx->dprm.static_in_smem = (ns > 0 && obstacle_table_bytes(ns, ng, ngp) <= 96 * 1024) ? 1 : 0;
   int rc = configure_launch(ctx);
   if (rc != CLRRT_OK) return rc;
   return upload_params(ctx);
@@ -385,7 +430,8 @@ int clrrt_tree_reset(clrrt_ctx* ctx, const clrrt_node* host, int n) {
     r.rf[0] = host[i].ref_front[0]; r.rf[1] = host[i].ref_front[1];
     r.rb[0] = host[i].ref_back[0]; r.rb[1] = host[i].ref_back[1];
     r.vback = host[i].ref_vback; r.costE = host[i].costE; r.costS = host[i].costS;
-    r.parent = host[i].parent; r.goal = host[i].goal_reached; r.nref = host[i].n_ref; r.sample = -1;
+    r.parent = host[i].parent; r.goal = host[i].goal_reached; r.nref = host[i].n_ref; r.kind = host[i].kind;
+    r.smp[0] = host[i].sample[0]; r.smp[1] = host[i].sample[1];
   }
   NodeRecord* d_tmp = nullptr;
   CK(cudaMalloc((void**)&d_tmp, (size_t)n * sizeof(NodeRecord)));
@@ -412,19 +458,20 @@ int clrrt_tree_download_range(clrrt_ctx* ctx, int first, int n, clrrt_node* host
   if (!ctx || !host || first < 0 || n < 0 || first + n > ctx->n_tree) return CLRRT_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   if (n == 0) return CLRRT_OK;
-  std::vector<double> d((size_t)n * 15);
+  std::vector<double> d((size_t)n * 17);
   std::vector<float> f((size_t)n * 2);
-  std::vector<int32_t> q((size_t)n * 3);
-  const double* dsrc[15] = {ctx->tree.x, ctx->tree.y, ctx->tree.th, ctx->tree.de, ctx->tree.v, ctx->tree.a, ctx->tree.t,
+  std::vector<int32_t> q((size_t)n * 4);
+  const double* dsrc[17] = {ctx->tree.x, ctx->tree.y, ctx->tree.th, ctx->tree.de, ctx->tree.v, ctx->tree.a, ctx->tree.t,
                             ctx->tree.s7, ctx->tree.s8, ctx->tree.s9, ctx->tree.rfx, ctx->tree.rfy, ctx->tree.rbx,
-                            ctx->tree.rby, ctx->tree.vback};
+                            ctx->tree.rby, ctx->tree.vback, ctx->tree.smx, ctx->tree.smy};
   cudaStream_t st = ctx->stream;
-  for (int k = 0; k < 15; k++) CK(cudaMemcpyAsync(d.data() + (size_t)k * n, dsrc[k] + first, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  for (int k = 0; k < 17; k++) CK(cudaMemcpyAsync(d.data() + (size_t)k * n, dsrc[k] + first, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(f.data(), ctx->tree.costE + first, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(f.data() + n, ctx->tree.costS + first, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(q.data(), ctx->tree.parent + first, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(q.data() + n, ctx->tree.goal + first, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(q.data() + 2 * (size_t)n, ctx->tree.nref + first, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(q.data() + 3 * (size_t)n, ctx->tree.kind + first, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   for (int i = 0; i < n; i++) {
     clrrt_node& o = host[i];
@@ -433,7 +480,8 @@ int clrrt_tree_download_range(clrrt_ctx* ctx, int first, int n, clrrt_node* host
     o.ref_back[0] = d[(size_t)12 * n + i]; o.ref_back[1] = d[(size_t)13 * n + i];
     o.ref_vback = d[(size_t)14 * n + i];
     o.costE = f[i]; o.costS = f[(size_t)n + i];
-    o.parent = q[i]; o.goal_reached = q[(size_t)n + i]; o.n_ref = q[2 * (size_t)n + i]; o.reserved = 0;
+    o.parent = q[i]; o.goal_reached = q[(size_t)n + i]; o.n_ref = q[2 * (size_t)n + i]; o.kind = q[3 * (size_t)n + i];
+    o.sample[0] = d[(size_t)15 * n + i]; o.sample[1] = d[(size_t)16 * n + i];
   }
   return CLRRT_OK;
 }
@@ -496,8 +544,14 @@ int clrrt_nearest_batch(clrrt_ctx* ctx, const double* sample_xy, const uint8_t* 
 
 int clrrt_propagate_batch(clrrt_ctx* ctx, const int32_t* parent, const double* sample_xy, const uint8_t* goal_biased,
                           int M, clrrt_rollout* out, double* traj, int traj_stride) {
+  return clrrt_propagate_batch_ex(ctx, parent, sample_xy, goal_biased, M, out, traj, traj_stride, nullptr, 0);
+}
+
+int clrrt_propagate_batch_ex(clrrt_ctx* ctx, const int32_t* parent, const double* sample_xy, const uint8_t* goal_biased,
+                             int M, clrrt_rollout* out, double* traj, int traj_stride, double* ref_xyv, int ref_stride) {
   if (!ctx || !parent || !sample_xy || !out || M < 1) return CLRRT_ERR_ARG;
   if (traj && traj_stride < 2) return CLRRT_ERR_ARG;
+  if (ref_xyv && ref_stride < 1) return CLRRT_ERR_ARG;
   if (!ctx->have_tree) return CLRRT_ERR_STATE;
   for (int i = 0; i < M; i++)
     if (parent[i] < 0 || parent[i] >= ctx->n_tree) return CLRRT_ERR_ARG;
@@ -521,6 +575,12 @@ int clrrt_propagate_batch(clrrt_ctx* ctx, const int32_t* parent, const double* s
     CK(cudaMalloc((void**)&b.d_traj, traj_elems * 8));
     b.traj_cap = traj_elems;
   }
+  const size_t ref_elems = ref_xyv ? (size_t)M * ref_stride * 3 : 0;
+  if (ref_elems > b.ref_cap) {
+    if (b.d_ref) cudaFree(b.d_ref);
+    CK(cudaMalloc((void**)&b.d_ref, ref_elems * 8));
+    b.ref_cap = ref_elems;
+  }
   std::vector<int32_t> l0, l1;
   for (int i = 0; i < M; i++) ((goal_biased && goal_biased[i]) ? l1 : l0).push_back(i);
   CK(cudaMemcpyAsync(b.d_parent, parent, (size_t)M * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -529,10 +589,13 @@ int clrrt_propagate_batch(clrrt_ctx* ctx, const int32_t* parent, const double* s
   if (!l1.empty()) CK(cudaMemcpyAsync(b.d_list1, l1.data(), l1.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(ctx->d_ints, 0, 4 * sizeof(int32_t), ctx->stream));
   if (traj) CK(cudaMemsetAsync(b.d_traj, 0, traj_elems * 8, ctx->stream));
+  if (ref_xyv) CK(cudaMemsetAsync(b.d_ref, 0, ref_elems * 8, ctx->stream));
   RolloutJob job;
   memset(&job, 0, sizeof job);
+  job.n_samples = M; job.n_ranks = 1;
   job.cand = b.d_parent; job.count = nullptr; job.cand_stride = 1; job.sample_xy = b.d_samples;
   job.parents = ctx->tree; job.out_records = b.d_out; job.traj = traj ? b.d_traj : nullptr; job.traj_stride = traj_stride;
+  job.ref_out = ref_xyv ? b.d_ref : nullptr; job.ref_stride = ref_stride;
   job.counters = ctx->d_counters; job.refill_min = ctx->refill_min;
   if (!l0.empty()) {
     job.n_items = (int)l0.size(); job.item_list = b.d_list0; job.head = ctx->d_ints + 0;
@@ -544,6 +607,7 @@ int clrrt_propagate_batch(clrrt_ctx* ctx, const int32_t* parent, const double* s
   }
   CK(cudaMemcpyAsync(out, b.d_out, (size_t)M * sizeof(clrrt_rollout), cudaMemcpyDeviceToHost, ctx->stream));
   if (traj) CK(cudaMemcpyAsync(traj, b.d_traj, traj_elems * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ref_xyv) CK(cudaMemcpyAsync(ref_xyv, b.d_ref, ref_elems * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return CLRRT_OK;
 }
@@ -570,37 +634,43 @@ int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint
   // 1. candidate parents
   if ((rc = nearest_dev(ctx, d_sample_xy, d_heuristic, K, ctx->d_cand, nullptr, ctx->d_count))) return rc;
   CK(cudaEventRecord(ctx->ev[1], st));
-  // 2. rollouts in candidate order until the first success
+  // 2. rollouts of all candidates, rank-major, with early skip: equivalent to trying them in order until the first success
   CK(cudaMemsetAsync(ctx->d_ints, 0, 4 * sizeof(int32_t), st));
-  CK(cudaMemsetAsync(ctx->d_valid, 0, 2 * (size_t)K * sizeof(int32_t), st));
+  CK(cudaMemsetAsync(ctx->d_best, 0x7f, (size_t)K * sizeof(int32_t), st));
   CK(cudaMemcpyAsync(ctx->h_counters + 8, ctx->d_counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   RolloutJob job;
   memset(&job, 0, sizeof job);
-  job.n_items = K; job.head = ctx->d_ints + 0; job.cand = ctx->d_cand; job.count = ctx->d_count;
+  job.n_samples = K; job.n_ranks = CLRRT_SORT_LIMIT; job.n_items = K * CLRRT_SORT_LIMIT;
+  job.head = ctx->d_ints + 0; job.cand = ctx->d_cand; job.count = ctx->d_count;
   job.cand_stride = CLRRT_SORT_LIMIT; job.sample_xy = d_sample_xy; job.parents = ctx->tree;
+  job.best_rank = ctx->d_best; job.res_code = ctx->d_res_code; job.res_steps = ctx->d_res_steps;
   job.out_nodes = ctx->stage; job.out_offset = 0; job.out_valid = ctx->d_valid;
-  job.gb_list = ctx->d_gb_list; job.gb_count = ctx->d_ints + 2;
-  job.counters = ctx->d_counters; job.refill_min = ctx->refill_min;
-  if ((rc = launch_rollout<false>(ctx, job, K))) return rc;
+  job.counters = nullptr; job.refill_min = ctx->refill_min;
+  if ((rc = launch_rollout<false>(ctx, job, job.n_items))) return rc;
+  SelectArgs sa;
+  sa.K = K; sa.n_ranks = CLRRT_SORT_LIMIT; sa.count = ctx->d_count; sa.best_rank = ctx->d_best;
+  sa.res_code = ctx->d_res_code; sa.res_steps = ctx->d_res_steps; sa.stage = ctx->stage; sa.valid = ctx->d_valid;
+  sa.slot = ctx->d_slot; sa.gb_list = ctx->d_gb_list; sa.gb_count = ctx->d_ints + 2; sa.counters = ctx->d_counters;
+  select_kernel<<<(K + 255) / 256, 256, 0, st>>>(sa);
+  CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev[2], st));
-  // 3. goal-biased rollout from every node just accepted that passes feasibleGoalBias
-  CK(cudaMemcpyAsync(ctx->h_ints + 2, ctx->d_ints + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  const int n_gb = ctx->h_ints[2];
-  if (n_gb > 0) {
+  // 3. goal-biased rollout from every node just accepted that passes feasibleGoalBias (item count stays on the device)
+  {
     RolloutJob g;
     memset(&g, 0, sizeof g);
-    g.n_items = n_gb; g.head = ctx->d_ints + 1; g.item_list = ctx->d_gb_list; g.parents = ctx->stage;
-    g.parent_offset = 0; g.parent_is_staged = 1; g.out_nodes = ctx->stage; g.out_offset = K; g.out_valid = ctx->d_valid;
+    g.n_items = K; g.n_items_dev = ctx->d_ints + 2; g.n_samples = K; g.n_ranks = 1;
+    g.head = ctx->d_ints + 1; g.item_list = ctx->d_gb_list; g.parent_slot = ctx->d_slot; g.parents = ctx->stage;
+    g.out_nodes = ctx->stage; g.out_offset = K * CLRRT_SORT_LIMIT; g.out_valid = ctx->d_valid + K;
     g.counters = ctx->d_counters; g.refill_min = ctx->refill_min;
-    if ((rc = launch_rollout<true>(ctx, g, n_gb))) return rc;
+    if ((rc = launch_rollout<true>(ctx, g, K))) return rc;
   }
   CK(cudaEventRecord(ctx->ev[3], st));
   // 4. compaction in sample order -> records -> append
   const int nblocks = (K + SCAN_THREADS - 1) / SCAN_THREADS;
   scan_block_sums_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(ctx->d_valid, K, ctx->d_block_sums);
   scan_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(ctx->d_block_sums, nblocks, ctx->d_ints + 3);
-  pack_records_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(ctx->stage, ctx->d_valid, K, ctx->d_block_sums, ctx->d_records, 0);
+  pack_records_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(ctx->stage, ctx->d_valid, K, ctx->d_block_sums, ctx->d_records,
+                                                         ctx->d_slot, K * CLRRT_SORT_LIMIT);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(ctx->h_ints + 3, ctx->d_ints + 3, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));

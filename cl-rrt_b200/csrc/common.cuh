@@ -29,15 +29,16 @@ struct NodeSoA {
   double *s7, *s8, *s9;                 // state[7..9] (logging slots: IDwp, v_ref, delta_cmd)
   double *rfx, *rfy, *rbx, *rby;        // ref.{x,y}.front(), ref.{x,y}.back()
   double *vback;                        // ref.v.back()
+  double *smx, *smy;                    // the sample this node's reference was aimed at (re-materialisation)
   float *costE, *costS;                 // float, as in struct Node
-  int32_t *parent, *goal, *nref;
+  int32_t *parent, *goal, *nref, *kind;
   // derived, for the nearest-node kernel (filled by derive_nodes_kernel)
   float *ca, *sa;                       // cosf/sinf of ang = (float)(-theta)   rrt/src/rrtplanner.cpp:378-380
   double *angPar;                       // atan2(ref back - ref front)          rrt/src/rrtplanner.cpp:273
 };
-#define NODE_SOA_DOUBLE_FIELDS 16
+#define NODE_SOA_DOUBLE_FIELDS 18
 #define NODE_SOA_FLOAT_FIELDS 4
-#define NODE_SOA_INT_FIELDS 3
+#define NODE_SOA_INT_FIELDS 4
 
 // ---- obstacle tables -------------------------------------------------------------------------------------
 // Static obstacles (vel == 0): the OBB of rrt/src/old_collisioncheck.cpp:6-22 does not depend on time, so the
@@ -79,7 +80,8 @@ struct DevParams {
   int32_t max_steps;     // number of i with i < 20/sim_dt, rrt/src/simulation.cpp:58
   int32_t obs_use_pred;
   int32_t n_static, n_moving;
-  int32_t n_static_pad;  // n_static rounded up to a multiple of 8 (broad-phase table is padded with never-near entries)
+  int32_t n_groups;      // static obstacles are sorted along a Z-order curve and grouped by 32 (broad phase)
+  int32_t n_groups_pad;  // group table length, a multiple of 32 (padded with never-near entries)
   int32_t static_in_smem;
   int32_t exact_dist;    // 1: return the reference's pseudo-distance (needed when W[2] != 0); 0: verdict only
   float veh_reach;       // half diagonal of the vehicle box (broad phase)

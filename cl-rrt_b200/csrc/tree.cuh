@@ -2,6 +2,7 @@
 //
 // Replaces MyRRT::addNode (rrt/include/rrt/rrtplanner.h:111-113) for a whole round: the rollout kernels leave
 // accepted nodes in a staging SoA (slot j = node from sample j, slot K+j = its goal-biased child), this file
+// (slot[j] = winning candidate of sample j among its n_ranks staging slots, gb_base + j = its goal-biased child)
 // compacts them in the order the sequential reference would have appended them (sample 0's node, its goal
 // child, sample 1's node, ...) into fixed-stride records, and appends records to the tree SoA.  Records are
 // also the unit of the multi-GPU exchange: every rank all-gathers its records and appends all ranks' chunks
@@ -16,8 +17,8 @@ struct __align__(16) NodeRecord {  // CLRRT_RECORD_BYTES
   double vback;
   float costE, costS;
   int32_t parent;   // tree index, or -2: "the record just before this one" (goal-biased child of the node before)
-  int32_t goal, nref, sample;
-  double pad[2];
+  int32_t goal, nref, kind;
+  double smp[2];    // sample the reference was aimed at
 };
 static_assert(sizeof(NodeRecord) == CLRRT_RECORD_BYTES, "record stride");
 
@@ -65,17 +66,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(int32_t* block_
   if (t == 0) *total = carry;
 }
 
-__device__ __forceinline__ void fill_record(NodeRecord& r, const NodeSoA& S, int k, int parent, int sample) {
+__device__ __forceinline__ void fill_record(NodeRecord& r, const NodeSoA& S, int k, int parent) {
   r.state[0] = S.x[k]; r.state[1] = S.y[k]; r.state[2] = S.th[k]; r.state[3] = S.de[k]; r.state[4] = S.v[k];
   r.state[5] = S.a[k]; r.state[6] = S.t[k]; r.state[7] = S.s7[k]; r.state[8] = S.s8[k]; r.state[9] = S.s9[k];
   r.rf[0] = S.rfx[k]; r.rf[1] = S.rfy[k]; r.rb[0] = S.rbx[k]; r.rb[1] = S.rby[k]; r.vback = S.vback[k];
   r.costE = S.costE[k]; r.costS = S.costS[k]; r.parent = parent; r.goal = S.goal[k]; r.nref = S.nref[k];
-  r.sample = sample; r.pad[0] = 0; r.pad[1] = 0;
+  r.kind = S.kind[k]; r.smp[0] = S.smx[k]; r.smp[1] = S.smy[k];
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 pack_records_kernel(NodeSoA stage, const int32_t* valid, int K, const int32_t* block_offsets, NodeRecord* records,
-                    int sample_base) {
+                    const int32_t* slot, int gb_base) {
   __shared__ int s_w[32];
   const int j = blockIdx.x * SCAN_THREADS + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -102,8 +103,8 @@ pack_records_kernel(NodeSoA stage, const int32_t* valid, int K, const int32_t* b
   }
   __syncthreads();
   int pos = block_offsets[blockIdx.x] + s_w[warp] + incl - c;
-  if (vm) { fill_record(records[pos], stage, j, stage.parent[j], sample_base + j); pos++; }
-  if (vg) fill_record(records[pos], stage, K + j, -2, sample_base + j);
+  if (vm) { const int sidx = slot[j]; fill_record(records[pos], stage, sidx, stage.parent[sidx]); pos++; }
+  if (vg) fill_record(records[pos], stage, gb_base + j, -2);
 }
 
 // records -> tree SoA at [first, first+n), plus the derived per-node quantities of the nearest-node search
@@ -118,7 +119,7 @@ __global__ void append_records_kernel(NodeSoA t, int first, const NodeRecord* __
   t.rfx[k] = r.rf[0]; t.rfy[k] = r.rf[1]; t.rbx[k] = r.rb[0]; t.rby[k] = r.rb[1]; t.vback[k] = r.vback;
   t.costE[k] = r.costE; t.costS[k] = r.costS;
   t.parent[k] = r.parent == -2 ? k - 1 : r.parent;
-  t.goal[k] = r.goal; t.nref[k] = r.nref;
+  t.goal[k] = r.goal; t.nref[k] = r.nref; t.kind[k] = r.kind; t.smx[k] = r.smp[0]; t.smy[k] = r.smp[1];
   const float ang = (float)(-r.state[2] - M_PI * 0.0);  // rrtplanner.cpp:378
   float s, c;
   ref_sincosf(ang, &s, &c);

@@ -1,0 +1,312 @@
+// clrrt_planner.cpp — implementation of the ROS-free host facade (see clrrt_planner.hpp).
+#include "clrrt_planner.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+namespace clrrt {
+
+namespace {
+void ck(clrrt_ctx* ctx, int rc, const char* what) {
+  if (rc != CLRRT_OK) throw Error(std::string(what) + " failed (" + std::to_string(rc) + "): " + (ctx ? clrrt_last_error(ctx) : ""));
+}
+// LinearSpacedVector, rrt/include/rrt/functions.h:11-21
+std::vector<double> LinearSpacedVector(double a, double b, std::size_t N) {
+  double h = (b - a) / static_cast<double>(N - 1);
+  std::vector<double> xs(N);
+  double val = a;
+  for (auto it = xs.begin(); it != xs.end(); ++it, val += h) *it = val;
+  return xs;
+}
+Node node_from_c(const clrrt_node& c) {
+  Node n;
+  n.state.assign(c.state, c.state + 10);
+  n.parentID = c.parent;
+  n.ref.x = {c.ref_front[0], c.ref_back[0]};
+  n.ref.y = {c.ref_front[1], c.ref_back[1]};
+  n.ref.v = {c.ref_vback};
+  n.costE = c.costE; n.costS = c.costS; n.goalReached = c.goal_reached != 0;
+  return n;
+}
+}  // namespace
+
+void Vehicle::setTalos() {  // rrt/include/rrt/vehicle.h:23-38
+  dmax = 0.5435; ddmax = 0.3294; Td = 0.3; Ta = 0.3; amin = -6; amax = 2; L = 2.885; Lrear = 1;
+  Lfront = 4.848 - Lrear; w = 2; b = 1.8; Vch = 20; rho = 4.77; Kus = 0.018;
+}
+void Vehicle::setPrius() {  // rrt/include/rrt/vehicle.h:39-60
+  dmax = 0.52; ddmax = 0.3294; Td = 0.3; Ta = 0.3; amin = -6; amax = 2; L = 2.7;
+  double lf = 1.0868, lr = 1.6132;
+  Lrear = 1; Lfront = 2.7 + 0.5; w = 2; b = lr; rho = 5.95;
+  double Cf = 22201, Cr = 22201, m = 950 + 640;
+  Kus = (m / L) * (lr / Cf - lf / Cr);
+  Vch = 20;
+}
+
+MyRRT::MyRRT(const std::vector<double>& _goalPose, const std::vector<double>& _laneShifts, const std::vector<double>& _Cxy,
+             const bool& _bend, const Vehicle& veh, const PlannerParams& prm, double vmax, double car_speed, int device,
+             int tree_capacity, int max_round)
+    : bend(_bend), goalPose(_goalPose), laneShifts(_laneShifts), Cxy(_Cxy) {
+  if (goalPose.size() < 4) throw Error("goalPose needs 4 entries");
+  if (bend) throw Error("bend=true (curved-road mode) is outside the accelerated path");
+  clrrt_default_params(&prm_);
+  clrrt_vehicle& v = prm_.veh;
+  v.dmax = veh.dmax; v.ddmax = veh.ddmax; v.Td = veh.Td; v.Ta = veh.Ta; v.amin = veh.amin; v.amax = veh.amax; v.L = veh.L;
+  v.w = veh.w; v.Lrear = veh.Lrear; v.Lfront = veh.Lfront; v.b = veh.b; v.Vch = veh.Vch; v.rho = veh.rho; v.Kus = veh.Kus;
+  prm_.sim_dt = prm.sim_dt; prm_.ctrl_tla = prm.ctrl_tla; prm_.ctrl_mindla = prm.ctrl_mindla; prm_.ctrl_dlavmin = prm.ctrl_dlavmin;
+  prm_.ctrl_Kp = prm.ctrl_Kp; prm_.ctrl_Ki = prm.ctrl_Ki; prm_.ref_int = prm.ref_int; prm_.ref_mindist = prm.ref_mindist;
+  // updateReferenceResolution(v), rrt/src/controller.cpp:18-21 (rrt/src/motionplanner.cpp:16)
+  prm_.ref_res = std::max(std::abs(car_speed) * prm.ref_int, prm.ref_mindist);
+  prm_.vmax = vmax;  // rrt/src/motionplanner.cpp:17
+  for (int i = 0; i < 5; i++) { prm_.Wcost[i] = prm.Wcost[i]; Wcost[i] = prm.Wcost[i]; }  // rrt/src/rrtplanner.cpp:14-18
+  for (int i = 0; i < 4; i++) prm_.goal[i] = goalPose[i];
+  prm_.obs_use_pred = prm.obs_use_pred ? 1 : 0;
+  int rc = clrrt_create(&prm_, device, tree_capacity, max_round, nullptr, &ctx_);
+  if (rc != CLRRT_OK) {
+    std::string msg = ctx_ ? clrrt_last_error(ctx_) : "no CUDA device";
+    if (ctx_) clrrt_destroy(ctx_);
+    ctx_ = nullptr;
+    throw Error("clrrt_create failed (" + std::to_string(rc) + "): " + msg + " — there is no CPU fallback");
+  }
+}
+MyRRT::~MyRRT() {
+  if (ctx_) clrrt_destroy(ctx_);
+}
+void MyRRT::addInitialNode(const std::vector<double>& state) {
+  // rrt/src/rrtplanner.cpp:21-37: reference (0,0) -> (1,0) with N = floor(1/0.1) points, v = state[4]
+  clrrt_node n;
+  memset(&n, 0, sizeof n);
+  for (int k = 0; k < 10 && k < (int)state.size(); k++) n.state[k] = state[k];
+  double xend{1}, yend{0}, res{0.1};
+  int N = floor(sqrt(pow(xend, 2) + pow(yend, 2)) / res);
+  std::vector<double> rx = LinearSpacedVector(0, xend, N), ry = LinearSpacedVector(0, yend, N);
+  n.ref_front[0] = rx.front(); n.ref_front[1] = ry.front(); n.ref_back[0] = rx.back(); n.ref_back[1] = ry.back();
+  n.ref_vback = state[4];
+  n.parent = -1; n.n_ref = N;
+  ck(ctx_, clrrt_tree_reset(ctx_, &n, 1), "clrrt_tree_reset");
+}
+void MyRRT::setObstacles(const std::vector<Obstacle2D>& d) {
+  det = d;
+  std::vector<clrrt_obstacle> o(d.size());
+  for (size_t i = 0; i < d.size(); i++)
+    o[i] = {d[i].obb.center.x, d[i].obb.center.y, d[i].obb.center.theta, d[i].obb.size_x, d[i].obb.size_y,
+            d[i].vel.linear.x, d[i].vel.linear.y};
+  ck(ctx_, clrrt_set_obstacles(ctx_, o.empty() ? nullptr : o.data(), (int)o.size()), "clrrt_set_obstacles");
+}
+int MyRRT::treeSize() const { return clrrt_tree_size(ctx_); }
+std::vector<Node> MyRRT::tree() const {
+  const int n = treeSize();
+  std::vector<clrrt_node> c((size_t)n);
+  int got = 0;
+  ck(ctx_, clrrt_tree_download(ctx_, c.data(), n, &got), "clrrt_tree_download");
+  std::vector<Node> out;
+  out.reserve(got);
+  for (int i = 0; i < got; i++) out.push_back(node_from_c(c[i]));
+  return out;
+}
+
+void initializeTree(MyRRT& RRT, const Vehicle&, std::vector<Node>& nodes, std::vector<double>& carState) {
+  // rrt/src/rrtplanner.cpp:39-48: four logging slots appended, empty committed path -> root node
+  carState.push_back(0); carState.push_back(0); carState.push_back(0); carState.push_back(0);
+  if (!nodes.empty()) throw Error("carried-over trees (commit_path=true) are outside this round's scope");
+  RRT.addInitialNode(carState);
+}
+
+clrrt_round_stats expandTree(Vehicle&, MyRRT& RRT, int K) {
+  std::vector<double> s(2 * (size_t)K);
+  std::vector<uint8_t> h((size_t)K);
+  clrrt_draw_samples(RRT.goalPose.data(), K, s.data(), h.data());  // rrtplanner.cpp:133-143 on rand()
+  clrrt_round_stats st;
+  ck(RRT.ctx(), clrrt_expand_round(RRT.ctx(), s.data(), h.data(), K, &st), "clrrt_expand_round");
+  return st;
+}
+
+namespace {
+// one rollout with trajectory and reference dumps -> stateArray + MyReference
+void rematerialise(const MyRRT& RRT, int parent, const double sxy[2], bool gb, clrrt_rollout& r, StateArray& states,
+                   MyReference& ref) {
+  const int tstride = CLRRT_MAX_STEPS_CAP, rstride = 2048;
+  std::vector<double> traj((size_t)tstride * 10), rxyv((size_t)rstride * 3);
+  const uint8_t g = gb ? 1 : 0;
+  const int32_t p = parent;
+  ck(RRT.ctx(), clrrt_propagate_batch_ex(RRT.ctx(), &p, sxy, &g, 1, &r, traj.data(), tstride, rxyv.data(), rstride),
+     "clrrt_propagate_batch_ex");
+  states.clear();
+  for (int i = 0; i <= r.n_steps && i < tstride; i++) states.emplace_back(traj.begin() + 10 * i, traj.begin() + 10 * (i + 1));
+  ref = MyReference();
+  for (int i = 0; i < r.n_ref && i < rstride; i++) {
+    ref.x.push_back(rxyv[3 * i]); ref.y.push_back(rxyv[3 * i + 1]); ref.v.push_back(rxyv[3 * i + 2]);
+  }
+  ref.dir = 1;
+}
+}  // namespace
+
+Simulation::Simulation(const MyRRT& RRT, int parent, const Point& sample, const Vehicle&, const bool& GoalBiased) {
+  clrrt_rollout r;
+  const double sxy[2] = {sample.x, sample.y};
+  rematerialise(RRT, parent, sxy, GoalBiased, r, stateArray, ref);
+  costE = r.costE; costS = r.costS; goalReached = r.goal_reached != 0; endReached = r.end_reached != 0; failCode = r.fail;
+}
+
+std::vector<Node> extractBestPath(MyRRT& RRT) {
+  const int n = RRT.treeSize();
+  std::vector<int32_t> ids((size_t)n);
+  int len = 0;
+  ck(RRT.ctx(), clrrt_best_path(RRT.ctx(), ids.data(), n, &len), "clrrt_best_path");
+  std::vector<Node> best;
+  if (len == 0) return best;  // "No solution was found!", rrtplanner.cpp:342-344
+  std::vector<clrrt_node> c((size_t)len);
+  for (int i = 0; i < len; i++) ck(RRT.ctx(), clrrt_tree_download_range(RRT.ctx(), ids[i], 1, &c[i]), "download");
+  for (int i = 0; i < len; i++) best.push_back(node_from_c(c[i]));
+  // Node::tra / Node::ref: the device tree keeps end points only.  Every node records the sample its reference was
+  // aimed at and whether it was a goal-biased expansion, which with its parent re-creates the rollout exactly.
+  best[0].tra = {best[0].state};  // root: addInitialNode stores the single start state (rrtplanner.cpp:34)
+  for (int i = 1; i < len; i++) {
+    if (c[i].kind == 0) { best[i].tra = {best[i].state}; continue; }
+    clrrt_rollout r;
+    rematerialise(RRT, ids[i - 1], c[i].sample, c[i].kind == 2, r, best[i].tra, best[i].ref);
+  }
+  return best;
+}
+
+std::vector<Path> convertNodesToPath(const std::vector<Node>& path) {
+  std::vector<Path> result;
+  for (auto it = path.begin(); it != path.end(); ++it) {
+    Path segment;
+    segment.ref = it->ref;
+    segment.tra = it->tra;
+    result.push_back(segment);
+  }
+  return result;
+}
+Trajectory generateMPCmessage(const std::vector<Path>& path) {
+  Trajectory tra;
+  for (auto it = path.begin(); it != path.end(); ++it) {
+    for (size_t i = 1; i < it->tra.size(); i++) {
+      tra.x.push_back(it->tra[i][0]); tra.y.push_back(it->tra[i][1]); tra.theta.push_back(it->tra[i][2]);
+      tra.delta.push_back(it->tra[i][3]); tra.v.push_back(it->tra[i][4]); tra.a.push_back(it->tra[i][5]);
+      tra.a_cmd.push_back(it->tra[i][8]); tra.d_cmd.push_back(it->tra[i][9]);
+    }
+  }
+  return tra;
+}
+void filterMPCmessage(Trajectory& msg) {
+  Trajectory f;
+  double interval = 5, d = 0;
+  for (size_t i = 1; i < msg.x.size(); i++) {
+    if (d == 0) {
+      f.x.push_back(msg.x[i]); f.y.push_back(msg.y[i]); f.theta.push_back(msg.theta[i]); f.v.push_back(msg.v[i]);
+      f.a.push_back(msg.a[i]); f.a_cmd.push_back(msg.a_cmd[i]); f.d_cmd.push_back(msg.d_cmd[i]);
+    }
+    d += sqrt(pow(msg.x[i] - msg.x[i - 1], 2) + pow(msg.y[i] - msg.y[i - 1], 2));
+    if (d >= interval) d = 0;
+  }
+  msg = f;
+}
+void transformNodesCarToworld(std::vector<Node>& nodes, const std::vector<double> carPose) {
+  auto pt = [&](double& Xc, double& Yc) {  // transformPointCarToWorld, rrt/src/transformations.cpp:13-17
+    double Xw = cos(carPose[2]) * Xc - sin(carPose[2]) * Yc + carPose[0];
+    double Yw = sin(carPose[2]) * Xc + cos(carPose[2]) * Yc + carPose[1];
+    Xc = Xw; Yc = Yw;
+  };
+  for (auto& n : nodes) {
+    pt(n.state[0], n.state[1]);
+    n.state[2] += carPose[2];
+    for (size_t i = 0; i < n.ref.x.size(); i++) pt(n.ref.x[i], n.ref.y[i]);
+    for (auto& s : n.tra) pt(s[0], s[1]);  // headings of the trajectory are left as they are, as upstream (:310-313)
+  }
+}
+
+bool MotionPlanner::updateObstacles() {
+  if (getobstacles) det = getobstacles();
+  return true;  // upstream falls off the end of a bool function (rrt/src/motionplanner.cpp:81-86)
+}
+void MotionPlanner::updateState(const std::vector<double>& msg_state) {
+  state.clear();
+  state.insert(state.begin(), msg_state.begin(), msg_state.end());
+  if (state.size() != 6) throw Error("state must have 6 entries [x,y,theta,delta,v,a]");
+}
+bool MotionPlanner::resetPlanner() {
+  motionplan.clear();
+  return true;
+}
+void MotionPlanner::planMotion(MotionRequest req) {
+  Vehicle veh; veh.setPrius();                                  // :13
+  std::vector<double> worldState = state;                       // :14
+  std::vector<double> carPose = worldState;                     // transformStateToLocal, transformations.cpp:143-147
+  carPose[0] = 0; carPose[1] = 0; carPose[2] = 0;
+  updateObstacles();                                            // :18
+  MyRRT RRT(req.goal, req.laneShifts, req.Cxy, req.bend, veh, params, req.vmax, carPose[4], device, 1 << 18,
+            std::max(samplesPerRound, 1));                      // :16-17, :23
+  RRT.setObstacles(det);                                        // :24
+  RRT.carState = carPose;
+  if (!params.commit_path) bestNodes.clear();                   // :28-30
+  initializeTree(RRT, veh, bestNodes, carPose);                 // :32
+  int iter = 0;                                                 // :39-43
+  auto t0 = std::chrono::steady_clock::now();
+  for (;; iter++) {
+    if (maxIterations >= 0) { if (iter >= maxIterations) break; }
+    else if (std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() >= budget_ms) break;
+    expandTree(veh, RRT, samplesPerRound);
+  }
+  lastIterations = iter;
+  lastTreeSize = RRT.treeSize();
+  clrrt_counters_get(RRT.ctx(), &lastCounters);                 // :45
+  bestNodes = extractBestPath(RRT);                             // :51
+  transformNodesCarToworld(bestNodes, worldState);              // :54
+  lastTrajectory = Trajectory();
+  if (bestNodes.size() == 0) return;                            // :56-58
+  std::vector<Path> plan = convertNodesToPath(bestNodes);       // :66
+  Trajectory msg = generateMPCmessage(plan);                    // :69
+  filterMPCmessage(msg);                                        // :70
+  lastTrajectory = msg;
+  if (msg.x.size() >= 3 && pubMPC) pubMPC(msg);                 // :71-74
+}
+
+}  // namespace clrrt
+
+extern "C" int clrrt_host_plan_motion(const double* car_state6, const double* goal4, double vmax, const clrrt_obstacle* obs,
+                                      int n_obs, int samples_per_round, int max_iterations, double budget_ms, unsigned seed,
+                                      int device, int* tree_size, int* iterations, clrrt_counters* counters, double* traj8,
+                                      int traj_cap, int* traj_len, int32_t* best_ids, int best_cap, int* best_len) {
+  try {
+    clrrt::MotionPlanner mp;
+    mp.device = device;
+    mp.samplesPerRound = samples_per_round;
+    mp.maxIterations = max_iterations;
+    mp.budget_ms = budget_ms;
+    std::vector<clrrt::Obstacle2D> det((size_t)n_obs);
+    for (int i = 0; i < n_obs; i++) {
+      det[i].obb.center.x = obs[i].cx; det[i].obb.center.y = obs[i].cy; det[i].obb.center.theta = obs[i].theta;
+      det[i].obb.size_x = obs[i].size_x; det[i].obb.size_y = obs[i].size_y;
+      det[i].vel.linear.x = obs[i].vx; det[i].vel.linear.y = obs[i].vy;
+    }
+    mp.getobstacles = [&]() { return det; };
+    mp.updateState(std::vector<double>(car_state6, car_state6 + 6));
+    clrrt::MotionRequest req;
+    req.goal.assign(goal4, goal4 + 4);
+    req.vmax = vmax;
+    req.laneShifts = {0};
+    srand(seed);  // the reference never seeds rand(): seed 1 reproduces it
+    mp.planMotion(req);
+    if (tree_size) *tree_size = mp.lastTreeSize;
+    if (iterations) *iterations = mp.lastIterations;
+    if (counters) *counters = mp.lastCounters;
+    const clrrt::Trajectory& t = mp.lastTrajectory;
+    const int n = (int)t.x.size();
+    if (traj_len) *traj_len = n;
+    for (int i = 0; i < n && i < traj_cap && traj8; i++) {
+      double* o = traj8 + 8 * i;
+      o[0] = t.x[i]; o[1] = t.y[i]; o[2] = t.theta[i]; o[3] = 0; o[4] = t.v[i]; o[5] = t.a[i]; o[6] = t.a_cmd[i]; o[7] = t.d_cmd[i];
+    }
+    if (best_len) *best_len = (int)mp.bestNodes.size();
+    (void)best_ids; (void)best_cap;
+    return CLRRT_OK;
+  } catch (const std::exception& e) {
+    fprintf(stderr, "clrrt_host_plan_motion: %s\n", e.what());
+    return CLRRT_ERR_STATE;
+  }
+}

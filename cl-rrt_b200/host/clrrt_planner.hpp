@@ -1,0 +1,176 @@
+// clrrt_planner.hpp — ROS-free C++ host facade over the C ABI (include/clrrt.h).
+//
+// Keeps the shapes of the reference's own C++ surface for the tree-expansion path so that its call sites read
+// the same (names, argument meaning, public result fields):
+//   Vehicle                         rrt/include/rrt/vehicle.h:5-61
+//   MyReference, Node, MyRRT        rrt/include/rrt/rrtplanner.h:27-80
+//   Simulation                      rrt/include/rrt/simulation.h:7-26   (all work in the constructor)
+//   MotionPlanner::planMotion / updateObstacles / updateState / resetPlanner
+//                                   rrt/include/rrt/motionplanner.h:20-42, rrt/src/motionplanner.cpp:8-100
+//   MotionRequest, Obstacle2D, Trajectory   car_msgs/msg/*.msg (plain structs, same field names)
+// The ROS pieces (publishers, the getobstacles service client) become std::function hooks.  All numerics run in
+// the CUDA library; this layer only marshals.  There is no CPU fallback: constructing a MyRRT without a CUDA
+// device throws.
+#pragma once
+#include <cstdint>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "clrrt.h"
+
+namespace clrrt {
+
+typedef std::vector<double> state_type;               // rrt/include/rrt/datatypes.h:11
+typedef std::vector<std::vector<double>> StateArray;  // rrt/include/rrt/datatypes.h:12
+
+struct Point { double x = 0, y = 0, z = 0; };  // geometry_msgs/Point
+
+// rrt/include/rrt/vehicle.h
+class Vehicle {
+ public:
+  double dmax, ddmax, Td, Ta, amin, amax, L, w, Lrear, Lfront, b, Vch, rho, Kus;
+  void setTalos();
+  void setPrius();
+};
+
+// car_msgs/msg/Obstacle2D.msg (vision_msgs/BoundingBox2D obb + geometry_msgs/Twist vel)
+struct Obstacle2D {
+  struct { struct { double x = 0, y = 0, theta = 0; } center; double size_x = 0, size_y = 0; } obb;
+  struct { struct { double x = 0, y = 0, z = 0; } linear, angular; } vel;
+};
+// car_msgs/msg/MotionRequest.msg
+struct MotionRequest {
+  std::vector<double> goal;
+  double vmax = 0;
+  bool bend = false;
+  std::vector<double> Cxy, Cxs, laneShifts;
+};
+// car_msgs/msg/Trajectory.msg
+struct Trajectory { std::vector<double> x, y, theta, delta, v, a, a_cmd, d_cmd; };
+
+// rrt/include/rrt/rrtplanner.h:27-33
+struct MyReference {
+  std::vector<double> x, y, v;
+  signed int dir = 1;
+  double aend = 0;
+};
+// rrt/include/rrt/rrtplanner.h:35-47.  ref holds front/back points (the device keeps no full paths); tra is filled
+// for the nodes of an extracted best path.
+struct Node {
+  std::vector<double> state;
+  signed int parentID = -1;
+  MyReference ref;
+  float costE = 0, costS = 0;
+  bool goalReached = false;
+  std::vector<state_type> tra;
+};
+struct Path {  // rrt/include/rrt/motionplanner.h:4-7
+  MyReference ref;
+  std::vector<state_type> tra;
+};
+
+struct PlannerParams {  // rrt/launch/parameters.launch:3-20 and rrt/src/rrt_node.cpp:2-24
+  double sim_dt = 0.04, ctrl_tla = 1.4, ctrl_mindla = 3.2, ctrl_dlavmin = 3, ctrl_Kp = 8, ctrl_Ki = 0.05;
+  double ref_int = 0.02, ref_mindist = 0.2;
+  double Wcost[5] = {10, 5, 0, 4, 1};
+  bool commit_path = false, obs_use_pred = true;
+};
+
+class Error : public std::runtime_error {
+ public:
+  using std::runtime_error::runtime_error;
+};
+
+// rrt/include/rrt/rrtplanner.h:51-80.  Owns one device context; `tree` lives on the GPU.
+class MyRRT {
+ public:
+  int sortLimit = CLRRT_SORT_LIMIT;
+  bool goalReached = false, bend = false;
+  std::vector<double> goalPose, laneShifts, Cxy;
+  signed int direction = 1;
+  std::vector<Obstacle2D> det;
+  std::vector<double> carState;
+  double Wcost[5];
+
+  MyRRT(const std::vector<double>& goalPose, const std::vector<double>& laneShifts, const std::vector<double>& Cxy,
+        const bool& bend, const Vehicle& veh, const PlannerParams& prm, double vmax, double car_speed, int device = 0,
+        int tree_capacity = 1 << 18, int max_round = 1 << 14);
+  ~MyRRT();
+  MyRRT(const MyRRT&) = delete;
+  MyRRT& operator=(const MyRRT&) = delete;
+
+  void addInitialNode(const std::vector<double>& state);  // rrt/src/rrtplanner.cpp:21-37
+  void setObstacles(const std::vector<Obstacle2D>& det);  // RRT.det = det, rrt/src/motionplanner.cpp:24
+  int treeSize() const;
+  std::vector<Node> tree() const;                          // download (ref = front/back points)
+  clrrt_ctx* ctx() const { return ctx_; }
+  const clrrt_params& params() const { return prm_; }
+
+ private:
+  clrrt_ctx* ctx_ = nullptr;
+  clrrt_params prm_;
+};
+
+// expandTree (rrt/src/rrtplanner.cpp:123-174), K samples per call against one tree snapshot.  K == 1 is the
+// reference's algorithm; samples come from sampleAroundVehicle on the C library's rand(), as upstream.
+clrrt_round_stats expandTree(Vehicle& veh, MyRRT& RRT, int K = 1);
+// extractBestPath (rrt/src/rrtplanner.cpp:318-368) with the trajectories of the returned nodes re-materialised.
+std::vector<Node> extractBestPath(MyRRT& RRT);
+// initializeTree (rrt/src/rrtplanner.cpp:39-48): empty committed path -> single root node
+void initializeTree(MyRRT& RRT, const Vehicle& veh, std::vector<Node>& nodes, std::vector<double>& carState);
+
+// rrt/include/rrt/simulation.h:7-26.  As upstream, everything happens in the constructor.  The rollout starts at
+// tree node `parent` (the reference passes that node's state and a reference built from it, rrtplanner.cpp:151-152)
+// towards `sample`; GoalBiased selects getGoalReference (rrtplanner.cpp:165-166).
+class Simulation {
+ public:
+  StateArray stateArray;
+  double costS = 0, costE = 0;
+  bool goalReached = false, endReached = false;
+  MyReference ref;  // x, y re-materialised on the host by LinearSpacedVector; v holds ref.v.back() only
+  int failCode = 0; // 0 none, 1 collision, 2 lateral acceleration, 3 iteration limit
+  Simulation(const MyRRT& RRT, int parent, const Point& sample, const Vehicle& veh, const bool& GoalBiased);
+  bool isvalid() const { return endReached; }
+};
+
+// rrt/include/rrt/motionplanner.h:20-42
+struct MotionPlanner {
+  std::vector<Path> motionplan;
+  std::vector<Node> bestNodes;
+  state_type state{0, 0, 0, 0, 0, 0};
+  std::vector<Obstacle2D> det;
+  // hooks replacing the ROS plumbing
+  std::function<std::vector<Obstacle2D>()> getobstacles;   // the "getobstacles" service, rrt/src/rrt_node.cpp:73
+  std::function<void(const Trajectory&)> pubMPC;           // "/path_publisher/path", rrt/src/rrt_node.cpp:63
+  PlannerParams params;
+  int device = 0;
+  int samplesPerRound = 1;        // 1 = the reference's sequential expandTree; >1 = snapshot rounds
+  double budget_ms = 200;         // Timer(200), rrt/src/motionplanner.cpp:39 (wall clock here, CPU time upstream)
+  int maxIterations = -1;         // >= 0: deterministic iteration budget instead of the timer (tests)
+  // results of the last query
+  Trajectory lastTrajectory;
+  int lastTreeSize = 0, lastIterations = 0;
+  clrrt_counters lastCounters{};
+
+  void planMotion(MotionRequest req);                       // rrt/src/motionplanner.cpp:8-77
+  bool updateObstacles();                                   // rrt/src/motionplanner.cpp:81-86
+  void updateState(const std::vector<double>& msg_state);   // rrt/src/motionplanner.cpp:89-94
+  bool resetPlanner();                                      // rrt/src/motionplanner.cpp:98-100
+};
+
+std::vector<Path> convertNodesToPath(const std::vector<Node>& path);   // rrt/src/motionplanner.cpp:264-275
+Trajectory generateMPCmessage(const std::vector<Path>& path);          // rrt/src/motionplanner.cpp:103-128
+void filterMPCmessage(Trajectory& msg);                                // rrt/src/motionplanner.cpp:130-150
+void transformNodesCarToworld(std::vector<Node>& nodes, const std::vector<double> carState);  // transformations.cpp:289-301
+
+}  // namespace clrrt
+
+// flat C view of the facade for bindings/tests (same library)
+extern "C" {
+int clrrt_host_plan_motion(const double* car_state6, const double* goal4, double vmax, const clrrt_obstacle* obs,
+                           int n_obs, int samples_per_round, int max_iterations, double budget_ms, unsigned seed,
+                           int device, int* tree_size, int* iterations, clrrt_counters* counters, double* traj8,
+                           int traj_cap, int* traj_len, int32_t* best_ids, int best_cap, int* best_len);
+}

@@ -70,7 +70,8 @@ typedef struct clrrt_node {
   int32_t parent;     /* parentID, -1 for the root */
   int32_t goal_reached;
   int32_t n_ref;      /* ref.x.size() */
-  int32_t reserved;
+  int32_t kind;       /* 0 root / uploaded, 1 expansion towards `sample` (rrtplanner.cpp:151-158), 2 goal-biased (:165-171) */
+  double sample[2];   /* the sample the node's reference was aimed at: with parent and kind it re-creates the rollout */
 } clrrt_node;
 
 /* Result of one Simulation (rrt/include/rrt/simulation.h:11-17) plus what expandTree derives from it. */
@@ -142,6 +143,12 @@ int clrrt_nearest_batch(clrrt_ctx* ctx, const double* sample_xy, const uint8_t* 
  * traj (optional, may be NULL) receives stateArray: M x traj_stride x 10 doubles, rows 0..n_steps. */
 int clrrt_propagate_batch(clrrt_ctx* ctx, const int32_t* parent, const double* sample_xy,
                           const uint8_t* goal_biased, int M, clrrt_rollout* out, double* traj, int traj_stride);
+/* Same, and additionally the generated references themselves (MyReference::x, y, v after generateVelocityProfile):
+ * ref_xyv (optional) receives M x ref_stride x 3 doubles, rows 0..n_ref-1.  This is how Node::tra and Node::ref of
+ * an extracted best path are re-materialised (the device tree keeps only end points). */
+int clrrt_propagate_batch_ex(clrrt_ctx* ctx, const int32_t* parent, const double* sample_xy,
+                             const uint8_t* goal_biased, int M, clrrt_rollout* out, double* traj, int traj_stride,
+                             double* ref_xyv, int ref_stride);
 
 /* == K iterations of expandTree (rrt/src/rrtplanner.cpp:123-174) against ONE tree snapshot: candidate search,
  * rollouts in candidate order until the first success, goal-biased rollout from the node just added, append in

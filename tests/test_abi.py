@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert clrrt.NODE_DTYPE.itemsize == 144
+    assert clrrt.NODE_DTYPE.itemsize == 160
     assert clrrt.ROLLOUT_DTYPE.itemsize == 160
     assert clrrt.OBSTACLE_DTYPE.itemsize == 56
     assert C.sizeof(clrrt.Vehicle) == 14 * 8
