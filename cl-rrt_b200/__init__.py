@@ -93,6 +93,7 @@ def load_library():
     lib.clrrt_round_records.argtypes = [vp, C.POINTER(vp), C.POINTER(ip)]
     lib.clrrt_append_records.argtypes = [vp, vp, vp, ip, ip]
     lib.clrrt_set_tuning.argtypes = [vp, ip, ip]
+    lib.clrrt_set_list_slack.argtypes = [vp, dp]
     lib.clrrt_tree_download_range.argtypes = [vp, ip, ip, vp]
     lib.clrrt_draw_samples.argtypes = [vp, ip, vp, vp]
     lib.srand = C.CDLL(None).srand
@@ -195,8 +196,11 @@ class Planner:
         o = np.ascontiguousarray(obstacles, dtype=np.float64).reshape(-1, 7)
         self._ck(self.lib.clrrt_set_obstacles(self.h, o.ctypes.data if len(o) else None, len(o)))
 
-    def set_tuning(self, refill_min=1, blocks_per_sm=0):
+    def set_tuning(self, refill_min=8, blocks_per_sm=0):
         self._ck(self.lib.clrrt_set_tuning(self.h, refill_min, blocks_per_sm))
+
+    def set_list_slack(self, metres):
+        self._ck(self.lib.clrrt_set_list_slack(self.h, float(metres)))
 
     # ---- tree -----------------------------------------------------------------------------------------
     def tree_reset(self, nodes):

@@ -52,6 +52,7 @@ struct clrrt_ctx {
   int32_t *d_best = nullptr, *d_slot = nullptr;
   uint8_t* d_res_code = nullptr;
   uint16_t* d_res_steps = nullptr;
+  double* d_ref_end = nullptr;
   float* d_key = nullptr;
   int32_t* d_ints = nullptr;  // [0] head main, [1] head gb, [2] gb_count, [3] total records, [4] best id
   int32_t* d_block_sums = nullptr;
@@ -63,7 +64,7 @@ struct clrrt_ctx {
   cudaEvent_t ev[6]{};
   int num_sms = 0, blocks_per_sm_main = 1, blocks_per_sm_gb = 1;
   size_t smem_bytes = 0;
-  int refill_min = 1;
+  int refill_min = 8;  // idle lanes a warp accumulates before fetching work (tuned on C3: 8 > 1 > 16)
   int blocks_override = 0;
   bool defer_append = false;
   int last_records = 0;
@@ -103,7 +104,8 @@ int alloc_soa(clrrt_ctx* ctx, NodeSoA& s, void** mem, int n) {
 }
 
 size_t obstacle_table_bytes(int n_static, int n_groups, int n_groups_pad) {
-  return (size_t)n_static * sizeof(ObsHot) + ((size_t)n_groups * 32 + (size_t)n_groups_pad) * sizeof(ObsBound);
+  (void)n_static;  // vertices / axes stay in global memory (read through L1 by the narrow phase only)
+  return ((size_t)n_groups * 32 + (size_t)n_groups_pad) * sizeof(ObsBound);
 }
 
 // host-side mirror of std::max semantics used by the reference's lookahead formulas
@@ -113,8 +115,10 @@ void fill_dev_params(clrrt_ctx* ctx) {
   const clrrt_params& p = ctx->prm;
   DevParams& d = ctx->dprm;
   const int ns = d.n_static, nm = d.n_moving, sm = d.static_in_smem, ng = d.n_groups, ngp = d.n_groups_pad;
+  const float vom = d.vobs_max;
+  const float lsl = d.list_slack > 0.0f ? d.list_slack : 1.0f;  // tuned on C3: 1.0 m (0.5 .. 3.0 within 10 %)
   memset(&d, 0, sizeof d);
-  d.n_static = ns; d.n_moving = nm; d.static_in_smem = sm; d.n_groups = ng; d.n_groups_pad = ngp;
+  d.n_static = ns; d.n_moving = nm; d.static_in_smem = sm; d.n_groups = ng; d.n_groups_pad = ngp; d.vobs_max = vom; d.list_slack = lsl;
   d.dmax = p.veh.dmax; d.ddmax = p.veh.ddmax; d.inv_Td = 1 / p.veh.Td; d.inv_Ta = 1 / p.veh.Ta;
   d.amin = p.veh.amin; d.amax = p.veh.amax; d.L = p.veh.L; d.Vch = p.veh.Vch; d.Kus = p.veh.Kus;
   d.sim_dt = p.sim_dt; d.mindla = p.ctrl_mindla; d.tla = p.ctrl_tla;
@@ -257,6 +261,7 @@ int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_r
   ok &= mal((void**)&ctx->d_slot, K * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_res_code, K * CLRRT_SORT_LIMIT);
   ok &= mal((void**)&ctx->d_res_steps, K * CLRRT_SORT_LIMIT * sizeof(uint16_t));
+  ok &= mal((void**)&ctx->d_ref_end, K * CLRRT_SORT_LIMIT * 2 * sizeof(double));
   ok &= mal((void**)&ctx->d_ints, 16 * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_block_sums, ((K + SCAN_THREADS - 1) / SCAN_THREADS + 1) * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_records, 2 * K * sizeof(NodeRecord));
@@ -279,7 +284,7 @@ int clrrt_destroy(clrrt_ctx* ctx) {
   if (!ctx) return CLRRT_ERR_ARG;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  void* ptrs[] = {ctx->tree_mem, ctx->stage_mem, ctx->d_grp, ctx->d_bnd, ctx->d_hot, ctx->d_best, ctx->d_res_code, ctx->d_res_steps, ctx->d_slot, ctx->d_cold, ctx->d_mov, ctx->d_samples, ctx->d_heur,
+  void* ptrs[] = {ctx->tree_mem, ctx->stage_mem, ctx->d_grp, ctx->d_bnd, ctx->d_hot, ctx->d_best, ctx->d_res_code, ctx->d_res_steps, ctx->d_slot, ctx->d_ref_end, ctx->d_cold, ctx->d_mov, ctx->d_samples, ctx->d_heur,
                   ctx->d_cand, ctx->d_key, ctx->d_count, ctx->d_valid, ctx->d_gb_list, ctx->d_ints, ctx->d_block_sums,
                   ctx->d_records, ctx->d_counters, ctx->batch.d_parent, ctx->batch.d_list0, ctx->batch.d_list1,
                   ctx->batch.d_samples, ctx->batch.d_out, ctx->batch.d_traj, ctx->batch.d_ref};
@@ -312,6 +317,7 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
   std::vector<ObsMoving> mov;
   const float margin = 0.1f;  // rollout.cuh: circles farther apart than this cannot collide in the reference's SAT
   const float vreach = ctx->dprm.veh_reach;
+  float vobs_max = 0.0f;
   for (int i = 0; i < n; i++) {
     const clrrt_obstacle& o = host[i];
     // getOBBvector, old_collisioncheck.cpp:14-16: OBB(centre, size_x/2, size_y/2, theta) with float w, h, o
@@ -348,7 +354,8 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
       ObsMoving m;
       m.cx = o.cx; m.cy = o.cy; m.vx = o.vx; m.vy = o.vy; m.ch = ch; m.sw = sw; m.sh = sh; m.cw = cw;
       const float r = reach + vreach + margin + 0.05f;  // + slack for the float centre prediction
-      m.R2 = r * r; m.pad[0] = m.pad[1] = m.pad[2] = 0;
+      m.R2 = r * r; m.pad[0] = r; m.pad[1] = m.pad[2] = 0;
+      vobs_max = std::max(vobs_max, (float)std::sqrt(o.vx * o.vx + o.vy * o.vy));
       mov.push_back(m);
     }
   }
@@ -371,12 +378,12 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
   std::vector<ObsHot> hot((size_t)std::max(ns, 1));
   std::vector<ObsCold> cold((size_t)std::max(ns, 1));
   std::vector<ObsBound> bnd((size_t)std::max(ng, 1) * 32), grp((size_t)ngp);
-  for (auto& b : bnd) { b.cx = 0; b.cy = 0; b.R2 = -1.0f; b.vxy_unused = 0; }
-  for (auto& g : grp) { g.cx = 0; g.cy = 0; g.R2 = -1.0f; g.vxy_unused = 0; }
+  for (auto& b : bnd) { b.cx = 0; b.cy = 0; b.R2 = -1.0f; b.reach = -1.0e30f; }
+  for (auto& g : grp) { g.cx = 0; g.cy = 0; g.R2 = -1.0f; g.reach = -1.0e30f; }
   for (int i = 0; i < ns; i++) {
     hot[i] = st[i].hot; cold[i] = st[i].cold;
     const float r = st[i].reach + vreach + margin;
-    bnd[i].cx = st[i].cx; bnd[i].cy = st[i].cy; bnd[i].R2 = r * r;
+    bnd[i].cx = st[i].cx; bnd[i].cy = st[i].cy; bnd[i].R2 = r * r; bnd[i].reach = r;
   }
   for (int g = 0; g < ng; g++) {
     const int lo = g * 32, hi = std::min(ns, lo + 32);
@@ -386,7 +393,7 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
     float R = 0;
     for (int i = lo; i < hi; i++) R = std::max(R, std::sqrt((st[i].cx - gx) * (st[i].cx - gx) + (st[i].cy - gy) * (st[i].cy - gy)) + st[i].reach);
     const float r = R + vreach + margin + 0.01f;
-    grp[g].cx = gx; grp[g].cy = gy; grp[g].R2 = r * r;
+    grp[g].cx = gx; grp[g].cy = gy; grp[g].R2 = r * r; grp[g].reach = r;
   }
   const int total = std::max<int>(32, n + 32);
   if (total > ctx->obs_cap) {
@@ -410,8 +417,9 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
   ctx->dprm.n_moving = (int)mov.size();
   ctx->dprm.n_groups = ng;
   ctx->dprm.n_groups_pad = ngp;
+  ctx->dprm.vobs_max = vobs_max * 1.001f;
   // bounds + vertices are staged in shared memory when they leave room for a second resident block
-  ctx->dprm.static_in_smem = (ns > 0 && obstacle_table_bytes(ns, ng, ngp) <= 96 * 1024) ? 1 : 0;
+  ctx->dprm.static_in_smem = (ns > 0 && obstacle_table_bytes(ns, ng, ngp) <= 64 * 1024) ? 1 : 0;
   int rc = configure_launch(ctx);
   if (rc != CLRRT_OK) return rc;
   return upload_params(ctx);
@@ -646,6 +654,10 @@ int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint
   job.best_rank = ctx->d_best; job.res_code = ctx->d_res_code; job.res_steps = ctx->d_res_steps;
   job.out_nodes = ctx->stage; job.out_offset = 0; job.out_valid = ctx->d_valid;
   job.counters = nullptr; job.refill_min = ctx->refill_min;
+  ref_end_kernel<<<(job.n_items + 255) / 256, 256, 0, st>>>(K, CLRRT_SORT_LIMIT, ctx->d_cand, CLRRT_SORT_LIMIT, ctx->d_count,
+                                                          d_sample_xy, nullptr, job.n_items, ctx->tree, ctx->d_ref_end);
+  CK(cudaGetLastError());
+  job.ref_end = ctx->d_ref_end;
   if ((rc = launch_rollout<false>(ctx, job, job.n_items))) return rc;
   SelectArgs sa;
   sa.K = K; sa.n_ranks = CLRRT_SORT_LIMIT; sa.count = ctx->d_count; sa.best_rank = ctx->d_best;
@@ -747,6 +759,13 @@ int clrrt_set_tuning(clrrt_ctx* ctx, int refill_min, int blocks_per_sm) {
   ctx->refill_min = refill_min;
   ctx->blocks_override = blocks_per_sm;
   return CLRRT_OK;
+}
+
+int clrrt_set_list_slack(clrrt_ctx* ctx, double metres) {
+  if (!ctx || !(metres > 0.0) || metres > 50.0) return CLRRT_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  ctx->dprm.list_slack = (float)metres;
+  return upload_params(ctx);
 }
 
 int clrrt_set_defer_append(clrrt_ctx* ctx, int defer) {

@@ -53,14 +53,14 @@ struct __align__(16) ObsCold {  // read only when the vehicle's own axes did not
 };
 // Broad-phase record (verdict-only mode, see rollout.cuh): centre and squared reach of the bounding circle.
 struct __align__(16) ObsBound {
-  float cx, cy, R2, vxy_unused;  // R2 = (half diagonal + vehicle half diagonal + margin)^2
+  float cx, cy, R2, reach;  // R2 = reach^2, reach = half diagonal + vehicle half diagonal + margin (R2 < 0: padding)
 };
 // Moving obstacles: centre = c + vel*t with t = x[6] of the lane, so vertices are rebuilt per step from
 // host-computed float half-extent products (the float operation order of setVertices is preserved).
 struct __align__(16) ObsMoving {
   double cx, cy, vx, vy;
   float ch, sw, sh, cw;  // cosf(o)*(h/2), sinf(o)*(w/2), sinf(o)*(h/2), cosf(o)*(w/2)
-  float R2, pad[3];      // broad phase: (half diagonal + vehicle half diagonal + margin)^2
+  float R2, pad[3];      // broad phase: R2 = reach^2, pad[0] = reach = half diagonal + vehicle half diagonal + margin
 };
 
 // ---- parameters in constant memory -----------------------------------------------------------------------
@@ -85,6 +85,8 @@ struct DevParams {
   int32_t static_in_smem;
   int32_t exact_dist;    // 1: return the reference's pseudo-distance (needed when W[2] != 0); 0: verdict only
   float veh_reach;       // half diagonal of the vehicle box (broad phase)
+  float vobs_max;        // speed of the fastest moving obstacle (candidate-list validity)
+  float list_slack;      // metres a vehicle may move before its candidate list is rebuilt
 };
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }

@@ -180,8 +180,10 @@ int clrrt_append_records(clrrt_ctx* ctx, const void* d_records, const int32_t* c
 
 int clrrt_get_device(const clrrt_ctx* ctx);
 /* Launch tuning of the rollout kernel: refill_min = idle lanes a warp accumulates before it fetches new work
- * (1 = refill immediately); blocks_per_sm = resident blocks of the persistent grid (0 = occupancy maximum). */
+ * (default 8; 1 = refill immediately); blocks_per_sm = resident blocks of the persistent grid (0 = occupancy maximum). */
 int clrrt_set_tuning(clrrt_ctx* ctx, int refill_min, int blocks_per_sm);
+/* Collision candidate lists: metres a vehicle may move before its list is rebuilt (default 1; results do not depend on it). */
+int clrrt_set_list_slack(clrrt_ctx* ctx, double metres);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,44 @@
+"""Turn gpurun_out/launches.csv and gpurun_out/prof.ncu-rep into the tracked summaries under profiles/."""
+import collections, csv, io, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+out = os.path.join(ROOT, "profiles")
+os.makedirs(out, exist_ok=True)
+rows = [r for r in csv.reader(open(os.path.join(ROOT, "gpurun_out", "launches.csv"))) if len(r) > 10]
+hdr = rows[0]; ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+agg = collections.OrderedDict()
+for r in rows[1:]:
+    agg.setdefault(r[ik].split("(")[0][:70], []).append(float(r[iv].replace(",", "")))
+tot = sum(sum(v) for v in agg.values())
+with open(os.path.join(out, f"{tag}_launches.md"), "w") as f:
+    f.write(f"# ncu launch list ({tag}): `python bench.py --steps 2 --warmup 1 --no-cpu-baseline`\n\n"
+            "`ncu --metrics gpu__time_duration.sum --clock-control none` — per-launch device time (cold-cache, serialised: compare shares).\n"
+            "Includes the untimed set-up (tree growth rounds of 8192 samples) and the e2e leg.\n\n| kernel | launches | total ms | max ms | share |\n|---|---|---|---|---|\n")
+    for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+        f.write(f"| `{k}` | {len(v)} | {sum(v)/1e6:.3f} | {max(v)/1e6:.3f} | {100*sum(v)/tot:.1f}% |\n")
+print(open(os.path.join(out, f"{tag}_launches.md")).read())
+rep = os.path.join(ROOT, "gpurun_out", "prof.ncu-rep")
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+r = list(csv.reader(io.StringIO(raw)))
+h = r[0]
+want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_fp64.sum", "sm__inst_executed_pipe_alu.sum", "sm__inst_executed_pipe_lsu.sum",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__warps_eligible.avg.per_cycle_active", "smsp__average_warp_latency_per_inst_issued.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum"]
+with open(os.path.join(out, f"{tag}_rollout_kernel_ncu.md"), "w") as f:
+    f.write(f"# ncu --set full ({tag}): rollout kernels of one C3 round (65536 samples, 1000 obstacles, 4096-node tree)\n\n"
+            "`ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 8 -c 2 python bench.py --steps 2 --warmup 1 --no-cpu-baseline`\n\n")
+    cols = [i for i in range(2, len(r))]
+    f.write("| metric | unit | " + " | ".join(f"launch {i-2}" for i in cols) + " |\n|---|---|" + "---|" * len(cols) + "\n")
+    for w in want:
+        if w in h:
+            i = h.index(w)
+            f.write(f"| {w} | {r[1][i]} | " + " | ".join(r[c][i][:60] for c in cols) + " |\n")
+print(open(os.path.join(out, f"{tag}_rollout_kernel_ncu.md")).read())

@@ -14,10 +14,14 @@ def run(tag, K=bench.K_ROUND, reps=2):
     for r in range(reps):
         st = pl.expand_round(smp[:K], heu[:K]); pl.tree_truncate(n0)
     print(f"{tag}: K={K} rollouts {st.rollouts} steps {st.sim_steps} ms nearest {st.ms_nearest:.2f} rollout {st.ms_rollout:.2f} goal {st.ms_goal:.2f} append {st.ms_append:.2f} -> {st.sim_steps/(st.ms_rollout+st.ms_goal)*1e3:.3e} steps/s (kernels), {st.sim_steps/(st.ms_rollout)*1e3:.3e} main only")
-for bps in (0, 1, 2):
+for bps in (0,):
     for rf in (1, 8, 16, 32):
         pl.set_tuning(refill_min=rf, blocks_per_sm=bps)
         run(f"blocks/SM={bps} refill_min={rf}")
+pl.set_tuning(refill_min=8, blocks_per_sm=0)
+for sl in (0.5, 1.0, 1.5, 2.0, 3.0):
+    pl.set_list_slack(sl); run(f"list slack {sl}")
+pl.set_list_slack(2.0)
 pl.set_tuning(refill_min=1, blocks_per_sm=0)
 for K in (4096, 16384, 65536):
     run("K sweep", K)
