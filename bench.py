@@ -174,6 +174,7 @@ def run_ours(args):
     h_smp = torch.from_numpy(smp).pin_memory()
     h_heu = torch.from_numpy(heu).pin_memory()
     if world > 1:
+        from clrrt_b200.exchange import gather_records
         pl.set_defer_append(True)
         rec_bytes = clrrt.RECORD_BYTES
         max_rec = 2 * K_ROUND
@@ -181,19 +182,14 @@ def run_ours(args):
         counts_t = torch.zeros(world, dtype=torch.int32, device="cuda")
 
     def exchange():
-        """per-round node all-gather over NCCL: per-rank counts, then fixed-stride records; every rank appends all
-        ranks' chunks in rank order (= global sample order), so the trees stay identical."""
+        """per-round node all-gather over NCCL (cl-rrt_b200/exchange.py): per-rank counts, then fixed-stride records;
+        every rank appends all ranks' chunks in rank order (= global sample order), so the trees stay identical."""
         ptr, n = pl.round_records()
-        mine = torch.tensor([n], dtype=torch.int32, device="cuda")
-        dist.all_gather_into_tensor(counts_t, mine)
-        counts = counts_t.cpu().numpy()
-        m = int(counts.max())
-        if m == 0:
+        src = _as_cuda_tensor(ptr, max_rec * rec_bytes, local)
+        out, counts, stride = gather_records(src, n, world, counts_t, gathered)
+        if stride == 0:
             return 0
-        src = _as_cuda_tensor(ptr, max_rec * rec_bytes, local)[:m * rec_bytes]
-        dst = gathered[:world * m * rec_bytes]
-        dist.all_gather_into_tensor(dst, src)
-        pl.append_records(dst.data_ptr(), counts, m)
+        pl.append_records(out.data_ptr(), counts, stride)
         return int(counts.sum())
 
     def one_round(dev_inputs=True):

@@ -151,12 +151,13 @@ Simulation::Simulation(const MyRRT& RRT, int parent, const Point& sample, const 
   costE = r.costE; costS = r.costS; goalReached = r.goal_reached != 0; endReached = r.end_reached != 0; failCode = r.fail;
 }
 
-std::vector<Node> extractBestPath(MyRRT& RRT) {
+std::vector<Node> extractBestPath(MyRRT& RRT, std::vector<int32_t>* ids_out) {
   const int n = RRT.treeSize();
   std::vector<int32_t> ids((size_t)n);
   int len = 0;
   ck(RRT.ctx(), clrrt_best_path(RRT.ctx(), ids.data(), n, &len), "clrrt_best_path");
   std::vector<Node> best;
+  if (ids_out) ids_out->assign(ids.begin(), ids.begin() + len);
   if (len == 0) return best;  // "No solution was found!", rrtplanner.cpp:342-344
   std::vector<clrrt_node> c((size_t)len);
   for (int i = 0; i < len; i++) ck(RRT.ctx(), clrrt_tree_download_range(RRT.ctx(), ids[i], 1, &c[i]), "download");
@@ -255,7 +256,11 @@ void MotionPlanner::planMotion(MotionRequest req) {
   lastIterations = iter;
   lastTreeSize = RRT.treeSize();
   clrrt_counters_get(RRT.ctx(), &lastCounters);                 // :45
-  bestNodes = extractBestPath(RRT);                             // :51
+  bestNodes = extractBestPath(RRT, &lastBestIds);               // :51
+  lastRematError = 0;
+  for (const Node& n : bestNodes)
+    if (!n.tra.empty())
+      for (int k = 0; k < 10; k++) lastRematError = std::max(lastRematError, std::abs(n.tra.back()[k] - n.state[k]));
   transformNodesCarToworld(bestNodes, worldState);              // :54
   lastTrajectory = Trajectory();
   if (bestNodes.size() == 0) return;                            // :56-58
@@ -271,7 +276,7 @@ void MotionPlanner::planMotion(MotionRequest req) {
 extern "C" int clrrt_host_plan_motion(const double* car_state6, const double* goal4, double vmax, const clrrt_obstacle* obs,
                                       int n_obs, int samples_per_round, int max_iterations, double budget_ms, unsigned seed,
                                       int device, int* tree_size, int* iterations, clrrt_counters* counters, double* traj8,
-                                      int traj_cap, int* traj_len, int32_t* best_ids, int best_cap, int* best_len) {
+                                      int traj_cap, int* traj_len, int32_t* best_ids, int best_cap, int* best_len, double* remat_err) {
   try {
     clrrt::MotionPlanner mp;
     mp.device = device;
@@ -302,8 +307,9 @@ extern "C" int clrrt_host_plan_motion(const double* car_state6, const double* go
       double* o = traj8 + 8 * i;
       o[0] = t.x[i]; o[1] = t.y[i]; o[2] = t.theta[i]; o[3] = 0; o[4] = t.v[i]; o[5] = t.a[i]; o[6] = t.a_cmd[i]; o[7] = t.d_cmd[i];
     }
-    if (best_len) *best_len = (int)mp.bestNodes.size();
-    (void)best_ids; (void)best_cap;
+    if (best_len) *best_len = (int)mp.lastBestIds.size();
+    for (int i = 0; i < (int)mp.lastBestIds.size() && i < best_cap && best_ids; i++) best_ids[i] = mp.lastBestIds[i];
+    if (remat_err) *remat_err = mp.lastRematError;
     return CLRRT_OK;
   } catch (const std::exception& e) {
     fprintf(stderr, "clrrt_host_plan_motion: %s\n", e.what());

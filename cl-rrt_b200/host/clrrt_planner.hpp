@@ -117,7 +117,7 @@ class MyRRT {
 // reference's algorithm; samples come from sampleAroundVehicle on the C library's rand(), as upstream.
 clrrt_round_stats expandTree(Vehicle& veh, MyRRT& RRT, int K = 1);
 // extractBestPath (rrt/src/rrtplanner.cpp:318-368) with the trajectories of the returned nodes re-materialised.
-std::vector<Node> extractBestPath(MyRRT& RRT);
+std::vector<Node> extractBestPath(MyRRT& RRT, std::vector<int32_t>* ids_out = nullptr);
 // initializeTree (rrt/src/rrtplanner.cpp:39-48): empty committed path -> single root node
 void initializeTree(MyRRT& RRT, const Vehicle& veh, std::vector<Node>& nodes, std::vector<double>& carState);
 
@@ -152,6 +152,8 @@ struct MotionPlanner {
   // results of the last query
   Trajectory lastTrajectory;
   int lastTreeSize = 0, lastIterations = 0;
+  std::vector<int32_t> lastBestIds;   // tree indices of bestNodes
+  double lastRematError = 0;          // max |tra.back() - node.state| over the best path (0: re-materialisation is exact)
   clrrt_counters lastCounters{};
 
   void planMotion(MotionRequest req);                       // rrt/src/motionplanner.cpp:8-77
@@ -172,5 +174,5 @@ extern "C" {
 int clrrt_host_plan_motion(const double* car_state6, const double* goal4, double vmax, const clrrt_obstacle* obs,
                            int n_obs, int samples_per_round, int max_iterations, double budget_ms, unsigned seed,
                            int device, int* tree_size, int* iterations, clrrt_counters* counters, double* traj8,
-                           int traj_cap, int* traj_len, int32_t* best_ids, int best_cap, int* best_len);
+                           int traj_cap, int* traj_len, int32_t* best_ids, int best_cap, int* best_len, double* remat_err);
 }
