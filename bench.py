@@ -221,7 +221,9 @@ def run_ours(args):
             tot_steps += st.sim_steps
             tot_roll += st.rollouts
             ms_roll += st.ms_rollout
-            launches += 7 + (1 if st.ms_goal > 0 else 0)
+            # nearest_topk, ref_end, rollout<main>, select, rollout<goal-biased>, scan_block_sums, scan_sums, pack_records,
+            # append_records (single GPU: appended inside the round; multi GPU: one append per rank chunk)
+            launches += 9 if world == 1 else 8 + world
         e1.record(stream)
         if world > 1:
             dist.barrier()

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_topk_kernel(const Nea
   __shared__ double s_nx[NEAREST_TILE], s_ny[NEAREST_TILE], s_rbx[NEAREST_TILE], s_rby[NEAREST_TILE];
   __shared__ double s_dpx[NEAREST_TILE], s_dpy[NEAREST_TILE], s_ang[NEAREST_TILE];
   __shared__ float s_ca[NEAREST_TILE], s_sa[NEAREST_TILE], s_ce[NEAREST_TILE];
+  __shared__ uint16_t s_idx[NEAREST_WARPS][NEAREST_TILE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x * NEAREST_WARPS + warp;
   const bool live = j < a.K;
@@ -109,8 +110,20 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_topk_kernel(const Nea
     }
     __syncthreads();
     if (live) {
-      for (int i = lane; i < n; i += 32) {
-        if (!feasible_node(sx, sy, s_rbx[i], s_rby[i], s_dpx[i], s_dpy[i], s_ang[i], a.feas_len)) continue;
+      // pass 1: feasibility of the tile's nodes for this sample; feasible ones are compacted into a per-warp index
+      // list with ballot/popc, so that the (much more expensive) key evaluation below runs on full warps
+      int cnt = 0;
+      for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        const bool f = i < n && feasible_node(sx, sy, s_rbx[i], s_rby[i], s_dpx[i], s_dpy[i], s_ang[i], a.feas_len);
+        const unsigned m = __ballot_sync(FULL_MASK, f);
+        if (f) s_idx[warp][cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+        cnt += __popc(m);
+      }
+      __syncwarp();
+      // pass 2: Dubins keys of the feasible nodes, per-lane sorted top-10 (a lane sees its nodes in increasing id order)
+      for (int q = lane; q < cnt; q += 32) {
+        const int i = s_idx[warp][q];
         float key = dubins_key(sx, sy, s_nx[i], s_ny[i], s_ca[i], s_sa[i]);
         if (optimize) key = s_ce[i] + key;  // rrtplanner.cpp:254
         if (key < k[CLRRT_SORT_LIMIT - 1]) {
@@ -125,6 +138,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_topk_kernel(const Nea
           }
         }
       }
+      __syncwarp();
     }
   }
   if (!live) return;
