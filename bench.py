@@ -165,7 +165,9 @@ def run_ours(args):
     # a dedicated (non-default) stream shared by torch and the library: torch.cuda.Event then times the library's kernels
     stream = torch.cuda.Stream(device=local)
     torch.cuda.set_stream(stream)
-    pl = clrrt.Planner(device=local, tree_capacity=TREE_SNAPSHOT + 2 * K_ROUND * world + 1024, max_round=K_ROUND,
+    prm = clrrt.default_params()
+    prm.fp32 = 1 if args.fp32 else 0
+    pl = clrrt.Planner(params=prm, device=local, tree_capacity=TREE_SNAPSHOT + 2 * K_ROUND * world + 1024, max_round=K_ROUND,
                        stream=stream.cuda_stream)
     boxes, smp, heu = build_workload(pl, clrrt, rank, world)
     n0 = pl.tree_size()
@@ -277,8 +279,9 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64 rollout + f32 SAT/Dubins (the reference's mixture)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "samples_per_round_per_gpu": K_ROUND, "tree_nodes": n0, "obstacles": n_obs,
+        "dtype": ("f32 rollout (tolerance mode) + f32 SAT/Dubins" if args.fp32 else "f64 rollout + f32 SAT/Dubins (the reference's mixture)"),
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD if not args.fp32 else WORKLOAD.replace("fp64 parity mode", "fp32 mode"), "samples_per_round_per_gpu": K_ROUND, "tree_nodes": n0, "obstacles": n_obs,
                    "parallelism": f"samples sharded over {world} GPU(s), tree replicated, node all-gather per round" if world > 1 else "1 GPU",
                    "l2_policy": "per-round inputs+outputs (samples, candidate lists, staging SoA, records: ~40 MB) are rewritten every round; the kernel is compute-bound, no L2 flush needed"},
         "rollouts_per_s": tot_roll / (ms * 1e-3), "sim_steps_per_round": tot_steps / args.steps,
@@ -398,6 +401,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--fp32", action="store_true", help="fp32 rollout mode (tolerance mode; default is the fp64 parity mode)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -162,23 +162,36 @@ int ensure_params(clrrt_ctx* ctx) {
   return CLRRT_OK;
 }
 
-int configure_launch(clrrt_ctx* ctx) {
-  ctx->smem_bytes = ctx->dprm.static_in_smem ? obstacle_table_bytes(ctx->dprm.n_static, ctx->dprm.n_groups, ctx->dprm.n_groups_pad) : 0;
+template <typename R> int configure_launch_t(clrrt_ctx* ctx) {
   const int sm = (int)ctx->smem_bytes;
-  CK(cudaFuncSetAttribute(rollout_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  CK(cudaFuncSetAttribute(rollout_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  CK(cudaFuncSetAttribute(rollout_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  CK(cudaFuncSetAttribute(rollout_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(rollout_kernel<R, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(rollout_kernel<R, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(rollout_kernel<R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(rollout_kernel<R, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   int b0 = 1, b1 = 1;
   if (ctx->dprm.exact_dist) {
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rollout_kernel<false, true>, ROLLOUT_THREADS, ctx->smem_bytes));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, rollout_kernel<true, true>, ROLLOUT_THREADS, ctx->smem_bytes));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rollout_kernel<R, false, true>, ROLLOUT_THREADS, ctx->smem_bytes));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, rollout_kernel<R, true, true>, ROLLOUT_THREADS, ctx->smem_bytes));
   } else {
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rollout_kernel<false, false>, ROLLOUT_THREADS, ctx->smem_bytes));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, rollout_kernel<true, false>, ROLLOUT_THREADS, ctx->smem_bytes));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rollout_kernel<R, false, false>, ROLLOUT_THREADS, ctx->smem_bytes));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, rollout_kernel<R, true, false>, ROLLOUT_THREADS, ctx->smem_bytes));
   }
   ctx->blocks_per_sm_main = std::max(1, b0);
   ctx->blocks_per_sm_gb = std::max(1, b1);
+  return CLRRT_OK;
+}
+
+int configure_launch(clrrt_ctx* ctx) {
+  ctx->smem_bytes = ctx->dprm.static_in_smem ? obstacle_table_bytes(ctx->dprm.n_static, ctx->dprm.n_groups, ctx->dprm.n_groups_pad) : 0;
+  return ctx->prm.fp32 ? configure_launch_t<float>(ctx) : configure_launch_t<double>(ctx);
+}
+
+template <typename R, bool GB> int launch_rollout_t(clrrt_ctx* ctx, const RolloutJob& job, int blocks) {
+  if (ctx->dprm.exact_dist)
+    rollout_kernel<R, GB, true><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_grp, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov);
+  else
+    rollout_kernel<R, GB, false><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_grp, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov);
+  CK(cudaGetLastError());
   return CLRRT_OK;
 }
 
@@ -189,12 +202,7 @@ template <bool GB> int launch_rollout(clrrt_ctx* ctx, const RolloutJob& job, int
   int blocks = ctx->num_sms * per_sm;  // persistent grid: a multiple of the SM count
   const int needed = (n_items_hint + lanes_per_block - 1) / lanes_per_block;
   if (needed < blocks) blocks = std::max(1, needed);
-  if (ctx->dprm.exact_dist)
-    rollout_kernel<GB, true><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_grp, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov);
-  else
-    rollout_kernel<GB, false><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_grp, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov);
-  CK(cudaGetLastError());
-  return CLRRT_OK;
+  return ctx->prm.fp32 ? launch_rollout_t<float, GB>(ctx, job, blocks) : launch_rollout_t<double, GB>(ctx, job, blocks);
 }
 
 }  // namespace
@@ -304,8 +312,13 @@ int clrrt_get_device(const clrrt_ctx* ctx) { return ctx ? ctx->device : CLRRT_ER
 int clrrt_set_params(clrrt_ctx* ctx, const clrrt_params* p) {
   if (!ctx || !p) return CLRRT_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
+  const bool mode_changed = (ctx->prm.fp32 != 0) != (p->fp32 != 0);
   ctx->prm = *p;
   fill_dev_params(ctx);
+  if (mode_changed) {
+    int rc = configure_launch(ctx);
+    if (rc != CLRRT_OK) return rc;
+  }
   return upload_params(ctx);
 }
 

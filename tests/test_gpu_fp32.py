@@ -1,0 +1,58 @@
+"""fp32 mode (clrrt_params.fp32 = 1): the same kernels with the rollout arithmetic in float.  Not bit-comparable with the
+reference (which is double); the stated tolerances against the fp64 golden rollouts are:
+  * verdicts (accepted / fail code) agree for >= 99.5 % of rollouts (measured: 100 % of 2 x 4096);
+  * accepted rollouts that end on the same step: final position within 1 mm, heading within 1e-4 rad, costs within 1e-4
+    relative (measured: 8e-5 m, 8e-6 rad, 2e-5);
+  * a threshold crossed one step earlier or later moves the end of a rollout by one 0.04 s step (<= 0.2 m): allowed for
+    at most 1 % of accepted rollouts, never more than one step.
+Goal-biased rollouts are excluded from the tolerance statement: their junction-point interpolation is rounding noise
+in any precision."""
+import os
+
+import numpy as np
+import pytest
+
+from gpu_common import clrrt  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+NONE = np.zeros((0, 7))
+
+
+@pytest.mark.parametrize("name", ["obs", "live"])
+def test_fp32_rollouts_within_stated_tolerance(clrrt, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, "g1_rollouts.npz"))
+    p = clrrt.default_params()
+    p.fp32 = 1
+    pl = clrrt.Planner(params=p, device=0, tree_capacity=1 << 12, max_round=1 << 13)
+    pl.set_query(g["car"], g["goal"], 5.0)
+    pl.tree_reset_records(g["tree"])
+    pl.set_obstacles(g["obstacles"] if name == "obs" else NONE)
+    got = clrrt.rollouts_as_table(pl.propagate_batch(g["parent"], g["samples"]))
+    want = g[f"out_{name}"]
+    same = (got[:, 15] == want[:, 15]) & (got[:, 12] == want[:, 12]) & (got[:, 13] == want[:, 13])
+    assert same.mean() >= 0.995
+    acc = same & ((want[:, 12] + want[:, 13]) > 0)
+    dstep = np.abs(got[acc, 14] - want[acc, 14])
+    assert dstep.max() <= 1 and (dstep > 0).mean() <= 0.01
+    eq = acc & (got[:, 14] == want[:, 14])
+    assert np.hypot(got[eq, 0] - want[eq, 0], got[eq, 1] - want[eq, 1]).max() < 1e-3
+    assert np.abs(got[eq, 2] - want[eq, 2]).max() < 1e-4
+    assert np.abs(got[eq, 10] / want[eq, 10] - 1).max() < 1e-4 and np.abs(got[eq, 11] / want[eq, 11] - 1).max() < 1e-4
+    print(f"fp32 {name}: verdict agreement {same.mean():.4f}, {int(acc.sum())} accepted, {(dstep > 0).sum()} end one step apart")
+    pl.close()
+
+
+def test_fp32_round_runs_and_grows_a_tree(clrrt):
+    from cpulib import scene_c1_boxes
+    p = clrrt.default_params()
+    p.fp32 = 1
+    pl = clrrt.Planner(params=p, device=0, tree_capacity=1 << 15, max_round=1 << 12)
+    car, goal = (0, 0, 0, 0, 2, 0), (50, 0, 0, 0)
+    pl.set_query(car, goal, 5.0)
+    pl.set_obstacles(scene_c1_boxes())
+    pl.tree_reset(clrrt.root_node(car))
+    s, h = clrrt.draw_samples(goal, 4096, seed=3)
+    st = pl.expand_round(s, h)
+    assert st.nodes_added > 500 and st.tree_size == 1 + st.nodes_added
+    assert len(pl.best_path()) >= 2
+    pl.close()
