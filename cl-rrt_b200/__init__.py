@@ -93,7 +93,7 @@ def load_library():
     lib.clrrt_round_records.argtypes = [vp, C.POINTER(vp), C.POINTER(ip)]
     lib.clrrt_append_records.argtypes = [vp, vp, vp, ip, ip]
     lib.clrrt_set_tuning.argtypes = [vp, ip, ip]
-    lib.clrrt_set_list_slack.argtypes = [vp, dp]
+    lib.clrrt_set_grid_cell.argtypes = [vp, dp]
     lib.clrrt_tree_download_range.argtypes = [vp, ip, ip, vp]
     lib.clrrt_draw_samples.argtypes = [vp, ip, vp, vp]
     lib.srand = C.CDLL(None).srand
@@ -199,8 +199,8 @@ class Planner:
     def set_tuning(self, refill_min=8, blocks_per_sm=0):
         self._ck(self.lib.clrrt_set_tuning(self.h, refill_min, blocks_per_sm))
 
-    def set_list_slack(self, metres):
-        self._ck(self.lib.clrrt_set_list_slack(self.h, float(metres)))
+    def set_grid_cell(self, metres):
+        self._ck(self.lib.clrrt_set_grid_cell(self.h, float(metres)))
 
     # ---- tree -----------------------------------------------------------------------------------------
     def tree_reset(self, nodes):

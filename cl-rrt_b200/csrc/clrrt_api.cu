@@ -41,7 +41,10 @@ struct clrrt_ctx {
   void *tree_mem = nullptr, *stage_mem = nullptr;
   ObsHot* d_hot = nullptr;
   ObsBound* d_bnd = nullptr;
-  ObsBound* d_grp = nullptr;
+  int32_t* d_cell_start = nullptr;   // broad-phase grid (CSR): [cells + 1]
+  uint16_t* d_cell_items = nullptr;
+  size_t cell_start_cap = 0, cell_items_cap = 0;
+  double grid_cell = 1.0;            // requested cell size in metres (clrrt_set_grid_cell)
   ObsCold* d_cold = nullptr;
   ObsMoving* d_mov = nullptr;
   int obs_cap = 0;
@@ -103,9 +106,9 @@ int alloc_soa(clrrt_ctx* ctx, NodeSoA& s, void** mem, int n) {
   return CLRRT_OK;
 }
 
-size_t obstacle_table_bytes(int n_static, int n_groups, int n_groups_pad) {
-  (void)n_static;  // vertices / axes stay in global memory (read through L1 by the narrow phase only)
-  return ((size_t)n_groups * 32 + (size_t)n_groups_pad) * sizeof(ObsBound);
+size_t obstacle_table_bytes(int n_static) {
+  // vertices / axes / cell lists stay in global memory (read through L1)
+  return (size_t)n_static * sizeof(ObsBound);
 }
 
 // host-side mirror of std::max semantics used by the reference's lookahead formulas
@@ -114,11 +117,11 @@ inline double hmax(double a, double b) { return (a < b) ? b : a; }
 void fill_dev_params(clrrt_ctx* ctx) {
   const clrrt_params& p = ctx->prm;
   DevParams& d = ctx->dprm;
-  const int ns = d.n_static, nm = d.n_moving, sm = d.static_in_smem, ng = d.n_groups, ngp = d.n_groups_pad;
-  const float vom = d.vobs_max;
-  const float lsl = d.list_slack > 0.0f ? d.list_slack : 1.0f;  // tuned on C3: 1.0 m (0.5 .. 3.0 within 10 %)
+  const DevParams keep = d;  // obstacle-derived fields survive a parameter update
   memset(&d, 0, sizeof d);
-  d.n_static = ns; d.n_moving = nm; d.static_in_smem = sm; d.n_groups = ng; d.n_groups_pad = ngp; d.vobs_max = vom; d.list_slack = lsl;
+  d.n_static = keep.n_static; d.n_moving = keep.n_moving; d.static_in_smem = keep.static_in_smem;
+  d.grid_nx = keep.grid_nx; d.grid_ny = keep.grid_ny; d.grid_inv_cell = keep.grid_inv_cell;
+  d.grid_ox = keep.grid_ox; d.grid_oy = keep.grid_oy;
   d.dmax = p.veh.dmax; d.ddmax = p.veh.ddmax; d.inv_Td = 1 / p.veh.Td; d.inv_Ta = 1 / p.veh.Ta;
   d.amin = p.veh.amin; d.amax = p.veh.amax; d.L = p.veh.L; d.Vch = p.veh.Vch; d.Kus = p.veh.Kus;
   d.sim_dt = p.sim_dt; d.mindla = p.ctrl_mindla; d.tla = p.ctrl_tla;
@@ -182,15 +185,15 @@ template <typename R> int configure_launch_t(clrrt_ctx* ctx) {
 }
 
 int configure_launch(clrrt_ctx* ctx) {
-  ctx->smem_bytes = ctx->dprm.static_in_smem ? obstacle_table_bytes(ctx->dprm.n_static, ctx->dprm.n_groups, ctx->dprm.n_groups_pad) : 0;
+  ctx->smem_bytes = ctx->dprm.static_in_smem ? obstacle_table_bytes(ctx->dprm.n_static) : 0;
   return ctx->prm.fp32 ? configure_launch_t<float>(ctx) : configure_launch_t<double>(ctx);
 }
 
 template <typename R, bool GB> int launch_rollout_t(clrrt_ctx* ctx, const RolloutJob& job, int blocks) {
   if (ctx->dprm.exact_dist)
-    rollout_kernel<R, GB, true><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_grp, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov);
+    rollout_kernel<R, GB, true><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_cell_start, ctx->d_cell_items);
   else
-    rollout_kernel<R, GB, false><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_grp, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov);
+    rollout_kernel<R, GB, false><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_cell_start, ctx->d_cell_items);
   CK(cudaGetLastError());
   return CLRRT_OK;
 }
@@ -292,7 +295,7 @@ int clrrt_destroy(clrrt_ctx* ctx) {
   if (!ctx) return CLRRT_ERR_ARG;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  void* ptrs[] = {ctx->tree_mem, ctx->stage_mem, ctx->d_grp, ctx->d_bnd, ctx->d_hot, ctx->d_best, ctx->d_res_code, ctx->d_res_steps, ctx->d_slot, ctx->d_ref_end, ctx->d_cold, ctx->d_mov, ctx->d_samples, ctx->d_heur,
+  void* ptrs[] = {ctx->tree_mem, ctx->stage_mem, ctx->d_cell_start, ctx->d_cell_items, ctx->d_bnd, ctx->d_hot, ctx->d_best, ctx->d_res_code, ctx->d_res_steps, ctx->d_slot, ctx->d_ref_end, ctx->d_cold, ctx->d_mov, ctx->d_samples, ctx->d_heur,
                   ctx->d_cand, ctx->d_key, ctx->d_count, ctx->d_valid, ctx->d_gb_list, ctx->d_ints, ctx->d_block_sums,
                   ctx->d_records, ctx->d_counters, ctx->batch.d_parent, ctx->batch.d_list0, ctx->batch.d_list1,
                   ctx->batch.d_samples, ctx->batch.d_out, ctx->batch.d_traj, ctx->batch.d_ref};
@@ -325,12 +328,11 @@ int clrrt_set_params(clrrt_ctx* ctx, const clrrt_params* p) {
 int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
   if (!ctx || n < 0 || (n > 0 && !host)) return CLRRT_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  struct StaticObs { ObsHot hot; ObsCold cold; float cx, cy, reach; uint32_t key; };
+  struct StaticObs { ObsHot hot; ObsCold cold; float cx, cy, reach; double cxd, cyd; uint32_t key; };
   std::vector<StaticObs> st;
   std::vector<ObsMoving> mov;
   const float margin = 0.1f;  // rollout.cuh: circles farther apart than this cannot collide in the reference's SAT
   const float vreach = ctx->dprm.veh_reach;
-  float vobs_max = 0.0f;
   for (int i = 0; i < n; i++) {
     const clrrt_obstacle& o = host[i];
     // getOBBvector, old_collisioncheck.cpp:14-16: OBB(centre, size_x/2, size_y/2, theta) with float w, h, o
@@ -361,14 +363,13 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
         }
         c.pmax[k] = mx; c.pmin[k] = mn;
       }
-      s.cx = (float)o.cx; s.cy = (float)o.cy; s.reach = reach; s.key = 0;
+      s.cx = (float)o.cx; s.cy = (float)o.cy; s.cxd = o.cx; s.cyd = o.cy; s.reach = reach; s.key = 0;
       st.push_back(s);
     } else {
       ObsMoving m;
       m.cx = o.cx; m.cy = o.cy; m.vx = o.vx; m.vy = o.vy; m.ch = ch; m.sw = sw; m.sh = sh; m.cw = cw;
-      const float r = reach + vreach + margin + 0.05f;  // + slack for the float centre prediction
-      m.R2 = r * r; m.pad[0] = r; m.pad[1] = m.pad[2] = 0;
-      vobs_max = std::max(vobs_max, (float)std::sqrt(o.vx * o.vx + o.vy * o.vy));
+      m.R2 = 0; m.pad[0] = reach + margin + 0.05f;  // + slack for the float rounding of the predicted centre
+      m.pad[1] = m.pad[2] = 0;
       mov.push_back(m);
     }
   }
@@ -387,52 +388,93 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
     std::stable_sort(st.begin(), st.end(), [](const StaticObs& a, const StaticObs& b) { return a.key < b.key; });
   }
   const int ns = (int)st.size();
-  const int ng = (ns + 31) / 32, ngp = std::max(32, ((ng + 31) / 32) * 32);
   std::vector<ObsHot> hot((size_t)std::max(ns, 1));
   std::vector<ObsCold> cold((size_t)std::max(ns, 1));
-  std::vector<ObsBound> bnd((size_t)std::max(ng, 1) * 32), grp((size_t)ngp);
-  for (auto& b : bnd) { b.cx = 0; b.cy = 0; b.R2 = -1.0f; b.reach = -1.0e30f; }
-  for (auto& g : grp) { g.cx = 0; g.cy = 0; g.R2 = -1.0f; g.reach = -1.0e30f; }
+  std::vector<ObsBound> bnd((size_t)std::max(ns, 1));
+  // ---- broad-phase grid over vehicle-box-centre positions (rollout.cuh, warp_collide) ---------------------------
+  // Obstacle i can touch a vehicle centred at p only if |p - c_i| <= reach_i + vreach; the list of a cell holds
+  // every obstacle whose circle of radius R_i = reach_i + vreach + margin (+ 1 cm for the float cell lookup) meets
+  // the cell's square.  The grid covers the bounding box of the centres enlarged by max R_i: a vehicle outside it
+  // is out of reach of every static obstacle.
+  double gox = 0, goy = 0, cell = ctx->grid_cell;
+  int gnx = 1, gny = 1;
+  std::vector<int32_t> cell_start(2, 0);
+  std::vector<uint16_t> cell_items;
+  if (ns > 0) {
+    double x0 = st[0].cxd, x1 = st[0].cxd, y0 = st[0].cyd, y1 = st[0].cyd, Rmax = 0;
+    for (auto& s : st) {
+      x0 = std::min(x0, s.cxd); x1 = std::max(x1, s.cxd); y0 = std::min(y0, s.cyd); y1 = std::max(y1, s.cyd);
+      Rmax = std::max(Rmax, (double)s.reach + vreach + margin + 0.01);
+    }
+    gox = x0 - Rmax; goy = y0 - Rmax;
+    const double wx = (x1 + Rmax) - gox, wy = (y1 + Rmax) - goy;
+    while (std::ceil(wx / cell) * std::ceil(wy / cell) > 262144.0) cell *= 1.25;
+    gnx = std::max(1, (int)std::ceil(wx / cell)); gny = std::max(1, (int)std::ceil(wy / cell));
+    cell_start.assign((size_t)gnx * gny + 1, 0);
+    auto visit = [&](bool fill) {
+      for (int i = 0; i < ns; i++) {
+        const double rx = st[i].cxd - gox, ry = st[i].cyd - goy, R = (double)st[i].reach + vreach + margin + 0.01;
+        const int ix0 = std::max(0, (int)std::floor((rx - R) / cell)), ix1 = std::min(gnx - 1, (int)std::floor((rx + R) / cell));
+        const int iy0 = std::max(0, (int)std::floor((ry - R) / cell)), iy1 = std::min(gny - 1, (int)std::floor((ry + R) / cell));
+        for (int iy = iy0; iy <= iy1; iy++)
+          for (int ix = ix0; ix <= ix1; ix++) {
+            const double dx = std::max(std::max(ix * cell - rx, rx - (ix + 1) * cell), 0.0);
+            const double dy = std::max(std::max(iy * cell - ry, ry - (iy + 1) * cell), 0.0);
+            if (dx * dx + dy * dy > R * R) continue;
+            const size_t c = (size_t)iy * gnx + ix;
+            if (fill) cell_items[(size_t)cell_start[c]++] = (uint16_t)i;
+            else cell_start[c + 1]++;
+          }
+      }
+    };
+    visit(false);
+    for (size_t c = 0; c + 1 < cell_start.size(); c++) cell_start[c + 1] += cell_start[c];
+    cell_items.resize((size_t)cell_start.back());
+    visit(true);  // advances cell_start[c] to the end of cell c == start of cell c + 1
+    for (size_t c = cell_start.size() - 1; c > 0; c--) cell_start[c] = cell_start[c - 1];
+    cell_start[0] = 0;
+  }
   for (int i = 0; i < ns; i++) {
     hot[i] = st[i].hot; cold[i] = st[i].cold;
-    const float r = st[i].reach + vreach + margin;
-    bnd[i].cx = st[i].cx; bnd[i].cy = st[i].cy; bnd[i].R2 = r * r; bnd[i].reach = r;
-  }
-  for (int g = 0; g < ng; g++) {
-    const int lo = g * 32, hi = std::min(ns, lo + 32);
-    double sx = 0, sy = 0;
-    for (int i = lo; i < hi; i++) { sx += st[i].cx; sy += st[i].cy; }
-    const float gx = (float)(sx / (hi - lo)), gy = (float)(sy / (hi - lo));
-    float R = 0;
-    for (int i = lo; i < hi; i++) R = std::max(R, std::sqrt((st[i].cx - gx) * (st[i].cx - gx) + (st[i].cy - gy) * (st[i].cy - gy)) + st[i].reach);
-    const float r = R + vreach + margin + 0.01f;
-    grp[g].cx = gx; grp[g].cy = gy; grp[g].R2 = r * r; grp[g].reach = r;
+    bnd[i].cx = (float)(st[i].cxd - gox); bnd[i].cy = (float)(st[i].cyd - goy);
+    bnd[i].rr = st[i].reach + margin; bnd[i].pad = 0.0f;
   }
   const int total = std::max<int>(32, n + 32);
   if (total > ctx->obs_cap) {
-    void* old[] = {ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_bnd, ctx->d_grp};
+    void* old[] = {ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_bnd};
     for (void* q : old) if (q) cudaFree(q);
-    ctx->d_hot = nullptr; ctx->d_cold = nullptr; ctx->d_mov = nullptr; ctx->d_bnd = nullptr; ctx->d_grp = nullptr;
+    ctx->d_hot = nullptr; ctx->d_cold = nullptr; ctx->d_mov = nullptr; ctx->d_bnd = nullptr;
     CK(cudaMalloc((void**)&ctx->d_hot, total * sizeof(ObsHot)));
     CK(cudaMalloc((void**)&ctx->d_cold, total * sizeof(ObsCold)));
     CK(cudaMalloc((void**)&ctx->d_mov, total * sizeof(ObsMoving)));
-    CK(cudaMalloc((void**)&ctx->d_bnd, (size_t)(total + 32) * sizeof(ObsBound)));
-    CK(cudaMalloc((void**)&ctx->d_grp, (size_t)(((total + 31) / 32 + 31) / 32 * 32 + 32) * sizeof(ObsBound)));
+    CK(cudaMalloc((void**)&ctx->d_bnd, (size_t)total * sizeof(ObsBound)));
     ctx->obs_cap = total;
+  }
+  if (cell_start.size() > ctx->cell_start_cap) {
+    if (ctx->d_cell_start) cudaFree(ctx->d_cell_start);
+    ctx->d_cell_start = nullptr;
+    CK(cudaMalloc((void**)&ctx->d_cell_start, cell_start.size() * sizeof(int32_t)));
+    ctx->cell_start_cap = cell_start.size();
+  }
+  if (cell_items.size() + 1 > ctx->cell_items_cap) {
+    if (ctx->d_cell_items) cudaFree(ctx->d_cell_items);
+    ctx->d_cell_items = nullptr;
+    CK(cudaMalloc((void**)&ctx->d_cell_items, (cell_items.size() + 1) * sizeof(uint16_t)));
+    ctx->cell_items_cap = cell_items.size() + 1;
   }
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaMemcpy(ctx->d_hot, hot.data(), hot.size() * sizeof(ObsHot), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->d_cold, cold.data(), cold.size() * sizeof(ObsCold), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->d_bnd, bnd.data(), bnd.size() * sizeof(ObsBound), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(ctx->d_grp, grp.data(), grp.size() * sizeof(ObsBound), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_cell_start, cell_start.data(), cell_start.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  if (!cell_items.empty()) CK(cudaMemcpy(ctx->d_cell_items, cell_items.data(), cell_items.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
   if (!mov.empty()) CK(cudaMemcpy(ctx->d_mov, mov.data(), mov.size() * sizeof(ObsMoving), cudaMemcpyHostToDevice));
   ctx->dprm.n_static = ns;
   ctx->dprm.n_moving = (int)mov.size();
-  ctx->dprm.n_groups = ng;
-  ctx->dprm.n_groups_pad = ngp;
-  ctx->dprm.vobs_max = vobs_max * 1.001f;
-  // bounds + vertices are staged in shared memory when they leave room for a second resident block
-  ctx->dprm.static_in_smem = (ns > 0 && obstacle_table_bytes(ns, ng, ngp) <= 64 * 1024) ? 1 : 0;
+  ctx->dprm.grid_nx = gnx; ctx->dprm.grid_ny = gny; ctx->dprm.grid_inv_cell = (float)(1.0 / cell);
+  ctx->dprm.grid_ox = gox; ctx->dprm.grid_oy = goy;
+  // the broad-phase table is staged in shared memory when it leaves room for the other resident blocks
+  ctx->dprm.static_in_smem = (ns > 0 && obstacle_table_bytes(ns) <= 48 * 1024) ? 1 : 0;
   int rc = configure_launch(ctx);
   if (rc != CLRRT_OK) return rc;
   return upload_params(ctx);
@@ -774,11 +816,10 @@ int clrrt_set_tuning(clrrt_ctx* ctx, int refill_min, int blocks_per_sm) {
   return CLRRT_OK;
 }
 
-int clrrt_set_list_slack(clrrt_ctx* ctx, double metres) {
-  if (!ctx || !(metres > 0.0) || metres > 50.0) return CLRRT_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
-  ctx->dprm.list_slack = (float)metres;
-  return upload_params(ctx);
+int clrrt_set_grid_cell(clrrt_ctx* ctx, double metres) {
+  if (!ctx || !(metres >= 0.05) || metres > 1000.0) return CLRRT_ERR_ARG;
+  ctx->grid_cell = metres;  // takes effect at the next clrrt_set_obstacles
+  return CLRRT_OK;
 }
 
 int clrrt_set_defer_append(clrrt_ctx* ctx, int defer) {

@@ -51,16 +51,17 @@ struct __align__(16) ObsCold {  // read only when the vehicle's own axes did not
   float nx[4], ny[4];           // axes; ny[3] = 0 (never written upstream, "defined" variant)
   float pmax[4], pmin[4];       // the obstacle's own projection interval on each of its axes
 };
-// Broad-phase record (verdict-only mode, see rollout.cuh): centre and squared reach of the bounding circle.
+// Broad-phase record (verdict-only mode, see rollout.cuh): bounding circle of a static obstacle.  The centre is
+// stored RELATIVE to the grid origin (subtracted in double on the host) so that float keeps ~1e-4 m over any scene.
 struct __align__(16) ObsBound {
-  float cx, cy, R2, reach;  // R2 = reach^2, reach = half diagonal + vehicle half diagonal + margin (R2 < 0: padding)
+  float cx, cy, rr, pad;  // rr = half diagonal of the obstacle box + margin
 };
 // Moving obstacles: centre = c + vel*t with t = x[6] of the lane, so vertices are rebuilt per step from
 // host-computed float half-extent products (the float operation order of setVertices is preserved).
 struct __align__(16) ObsMoving {
   double cx, cy, vx, vy;
   float ch, sw, sh, cw;  // cosf(o)*(h/2), sinf(o)*(w/2), sinf(o)*(h/2), cosf(o)*(w/2)
-  float R2, pad[3];      // broad phase: R2 = reach^2, pad[0] = reach = half diagonal + vehicle half diagonal + margin
+  float R2, pad[3];      // broad phase: pad[0] = rr = half diagonal + margin (+ slack for the float prediction); R2 unused
 };
 
 // ---- parameters in constant memory -----------------------------------------------------------------------
@@ -80,13 +81,14 @@ struct DevParams {
   int32_t max_steps;     // number of i with i < 20/sim_dt, rrt/src/simulation.cpp:58
   int32_t obs_use_pred;
   int32_t n_static, n_moving;
-  int32_t n_groups;      // static obstacles are sorted along a Z-order curve and grouped by 32 (broad phase)
-  int32_t n_groups_pad;  // group table length, a multiple of 32 (padded with never-near entries)
   int32_t static_in_smem;
+  // uniform grid over vehicle-box-centre positions (broad phase, verdict-only mode): cell -> list of the static
+  // obstacles whose bounding circle can come within reach of a vehicle centred anywhere in the cell
+  int32_t grid_nx, grid_ny;
+  float grid_inv_cell;
+  double grid_ox, grid_oy;
   int32_t exact_dist;    // 1: return the reference's pseudo-distance (needed when W[2] != 0); 0: verdict only
   float veh_reach;       // half diagonal of the vehicle box (broad phase)
-  float vobs_max;        // speed of the fastest moving obstacle (candidate-list validity)
-  float list_slack;      // metres a vehicle may move before its candidate list is rebuilt
 };
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }

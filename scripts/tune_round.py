@@ -19,9 +19,9 @@ for bps in (0,):
         pl.set_tuning(refill_min=rf, blocks_per_sm=bps)
         run(f"blocks/SM={bps} refill_min={rf}")
 pl.set_tuning(refill_min=8, blocks_per_sm=0)
-for sl in (0.5, 1.0, 1.5, 2.0, 3.0):
-    pl.set_list_slack(sl); run(f"list slack {sl}")
-pl.set_list_slack(2.0)
+for sl in (0.5, 1.0, 2.0, 4.0):
+    pl.set_grid_cell(sl); pl.set_obstacles(boxes); run(f"grid cell {sl}")
+pl.set_grid_cell(1.0); pl.set_obstacles(boxes)
 pl.set_tuning(refill_min=1, blocks_per_sm=0)
 for K in (4096, 16384, 65536):
     run("K sweep", K)

@@ -187,12 +187,15 @@ def test_full_size_properties(clrrt, planner):
     want = orc.rollout_batch(par[sub], s[sub])
     ok = want[:, 16] >= 3  # random (parent, sample) pairs may give references shorter than 3 points: undefined upstream
     assert_rollouts_match(clrrt.rollouts_as_table(a[sub])[ok], want[ok], "C3 subset")
-    # launch tuning (work-refill threshold, persistent-grid size, candidate-list slack) must not change any result
+    # launch tuning (work-refill threshold, persistent-grid size, broad-phase cell size) must not change any result
     planner.set_tuning(refill_min=1, blocks_per_sm=1)
-    planner.set_list_slack(0.25)
+    planner.set_grid_cell(0.3)
+    planner.set_obstacles(boxes)
     c = planner.propagate_batch(par, s)
-    planner.set_list_slack(4.0)
+    planner.set_grid_cell(7.0)   # cells with more than 64 listed obstacles: the chunked broad phase
+    planner.set_obstacles(boxes)
     d = planner.propagate_batch(par, s)
     planner.set_tuning(refill_min=8, blocks_per_sm=0)
-    planner.set_list_slack(1.0)
+    planner.set_grid_cell(1.0)
+    planner.set_obstacles(boxes)
     assert a.tobytes() == c.tobytes() and a.tobytes() == d.tobytes()
