@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libclrrt_b200.so")
+LIB_PATH = os.environ.get("CLRRT_LIB") or os.path.join(_HERE, "libclrrt_b200.so")  # CLRRT_LIB: kernel-tuning builds only
 SORT_LIMIT = 10
 RECORD_BYTES = 160
 

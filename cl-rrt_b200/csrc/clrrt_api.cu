@@ -108,7 +108,7 @@ int alloc_soa(clrrt_ctx* ctx, NodeSoA& s, void** mem, int n) {
 
 size_t obstacle_table_bytes(int n_static) {
   // vertices / axes / cell lists stay in global memory (read through L1)
-  return (size_t)n_static * sizeof(ObsBound);
+  return ((size_t)n_static + 1) * sizeof(ObsBound);  // + the sentinel record that pads the cell lists
 }
 
 // host-side mirror of std::max semantics used by the reference's lookahead formulas
@@ -276,11 +276,11 @@ int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_r
   ok &= mal((void**)&ctx->d_ints, 16 * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_block_sums, ((K + SCAN_THREADS - 1) / SCAN_THREADS + 1) * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_records, 2 * K * sizeof(NodeRecord));
-  ok &= mal((void**)&ctx->d_counters, 8 * sizeof(unsigned long long));
+  ok &= mal((void**)&ctx->d_counters, 16 * sizeof(unsigned long long));
   ok &= cudaMallocHost((void**)&ctx->h_ints, 16 * sizeof(int32_t)) == cudaSuccess;
   ok &= cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(unsigned long long)) == cudaSuccess;
   if (!ok) { ctx->err = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()); return fail(CLRRT_ERR_CUDA); }
-  cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream);
+  cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), ctx->stream);
   cudaMemsetAsync(ctx->d_ints, 0, 16 * sizeof(int32_t), ctx->stream);
   for (auto& e : ctx->ev) cudaEventCreate(&e);
   fill_dev_params(ctx);
@@ -328,7 +328,7 @@ int clrrt_set_params(clrrt_ctx* ctx, const clrrt_params* p) {
 int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
   if (!ctx || n < 0 || (n > 0 && !host)) return CLRRT_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  struct StaticObs { ObsHot hot; ObsCold cold; float cx, cy, reach; double cxd, cyd; uint32_t key; };
+  struct StaticObs { ObsHot hot; ObsCold cold; float cx, cy, reach, ohh, ohw, oc, os; double cxd, cyd; uint32_t key; };
   std::vector<StaticObs> st;
   std::vector<ObsMoving> mov;
   const float margin = 0.1f;  // rollout.cuh: circles farther apart than this cannot collide in the reference's SAT
@@ -364,12 +364,13 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
         c.pmax[k] = mx; c.pmin[k] = mn;
       }
       s.cx = (float)o.cx; s.cy = (float)o.cy; s.cxd = o.cx; s.cyd = o.cy; s.reach = reach; s.key = 0;
+      s.ohh = h / 2; s.ohw = w / 2; s.oc = co; s.os = so;
       st.push_back(s);
     } else {
       ObsMoving m;
       m.cx = o.cx; m.cy = o.cy; m.vx = o.vx; m.vy = o.vy; m.ch = ch; m.sw = sw; m.sh = sh; m.cw = cw;
-      m.R2 = 0; m.pad[0] = reach + margin + 0.05f;  // + slack for the float rounding of the predicted centre
-      m.pad[1] = m.pad[2] = 0;
+      m.rr = reach + margin + 0.05f;  // + slack for the float rounding of the predicted centre
+      m.ohh = h / 2; m.ohw = w / 2; m.oc = co; m.os = so; m.pad0 = m.pad1 = m.pad2 = 0;
       mov.push_back(m);
     }
   }
@@ -390,7 +391,7 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
   const int ns = (int)st.size();
   std::vector<ObsHot> hot((size_t)std::max(ns, 1));
   std::vector<ObsCold> cold((size_t)std::max(ns, 1));
-  std::vector<ObsBound> bnd((size_t)std::max(ns, 1));
+  std::vector<ObsBound> bnd((size_t)ns + 1);
   // ---- broad-phase grid over vehicle-box-centre positions (rollout.cuh, warp_collide) ---------------------------
   // Obstacle i can touch a vehicle centred at p only if |p - c_i| <= reach_i + vreach; the list of a cell holds
   // every obstacle whose circle of radius R_i = reach_i + vreach + margin (+ 1 cm for the float cell lookup) meets
@@ -411,6 +412,7 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
     while (std::ceil(wx / cell) * std::ceil(wy / cell) > 262144.0) cell *= 1.25;
     gnx = std::max(1, (int)std::ceil(wx / cell)); gny = std::max(1, (int)std::ceil(wy / cell));
     cell_start.assign((size_t)gnx * gny + 1, 0);
+    int32_t* fill_cursor = nullptr;
     auto visit = [&](bool fill) {
       for (int i = 0; i < ns; i++) {
         const double rx = st[i].cxd - gox, ry = st[i].cyd - goy, R = (double)st[i].reach + vreach + margin + 0.01;
@@ -422,23 +424,29 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
             const double dy = std::max(std::max(iy * cell - ry, ry - (iy + 1) * cell), 0.0);
             if (dx * dx + dy * dy > R * R) continue;
             const size_t c = (size_t)iy * gnx + ix;
-            if (fill) cell_items[(size_t)cell_start[c]++] = (uint16_t)i;
+            if (fill) cell_items[(size_t)fill_cursor[c]++] = (uint16_t)i;
             else cell_start[c + 1]++;
           }
       }
     };
     visit(false);
-    for (size_t c = 0; c + 1 < cell_start.size(); c++) cell_start[c + 1] += cell_start[c];
-    cell_items.resize((size_t)cell_start.back());
-    visit(true);  // advances cell_start[c] to the end of cell c == start of cell c + 1
-    for (size_t c = cell_start.size() - 1; c > 0; c--) cell_start[c] = cell_start[c - 1];
+    // lists are padded to whole blocks of 8 ids; cell_start is kept in blocks
+    std::vector<int32_t> cnt(cell_start.begin() + 1, cell_start.end());
     cell_start[0] = 0;
+    for (size_t c = 0; c < cnt.size(); c++) cell_start[c + 1] = cell_start[c] + (cnt[c] + 7) / 8;
+    cell_items.assign((size_t)cell_start.back() * 8, (uint16_t)ns);
+    std::vector<int32_t> fillpos(cnt.size());
+    for (size_t c = 0; c < cnt.size(); c++) fillpos[c] = cell_start[c] * 8;
+    fill_cursor = fillpos.data();
+    visit(true);
   }
   for (int i = 0; i < ns; i++) {
     hot[i] = st[i].hot; cold[i] = st[i].cold;
     bnd[i].cx = (float)(st[i].cxd - gox); bnd[i].cy = (float)(st[i].cyd - goy);
-    bnd[i].rr = st[i].reach + margin; bnd[i].pad = 0.0f;
+    bnd[i].rr = st[i].reach + margin; bnd[i].ohh = st[i].ohh; bnd[i].ohw = st[i].ohw;
+    bnd[i].oc = st[i].oc; bnd[i].os = st[i].os; bnd[i].pad = 0.0f;
   }
+  bnd[ns].cx = 0; bnd[ns].cy = 0; bnd[ns].rr = -1.0e30f; bnd[ns].ohh = 0; bnd[ns].oc = 1; bnd[ns].os = 0; bnd[ns].ohw = 0; bnd[ns].pad = 0;
   const int total = std::max<int>(32, n + 32);
   if (total > ctx->obs_cap) {
     void* old[] = {ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_bnd};
@@ -447,7 +455,7 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
     CK(cudaMalloc((void**)&ctx->d_hot, total * sizeof(ObsHot)));
     CK(cudaMalloc((void**)&ctx->d_cold, total * sizeof(ObsCold)));
     CK(cudaMalloc((void**)&ctx->d_mov, total * sizeof(ObsMoving)));
-    CK(cudaMalloc((void**)&ctx->d_bnd, (size_t)total * sizeof(ObsBound)));
+    CK(cudaMalloc((void**)&ctx->d_bnd, (size_t)(total + 1) * sizeof(ObsBound)));
     ctx->obs_cap = total;
   }
   if (cell_start.size() > ctx->cell_start_cap) {
@@ -456,11 +464,11 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
     CK(cudaMalloc((void**)&ctx->d_cell_start, cell_start.size() * sizeof(int32_t)));
     ctx->cell_start_cap = cell_start.size();
   }
-  if (cell_items.size() + 1 > ctx->cell_items_cap) {
+  if (cell_items.size() + 8 > ctx->cell_items_cap) {
     if (ctx->d_cell_items) cudaFree(ctx->d_cell_items);
     ctx->d_cell_items = nullptr;
-    CK(cudaMalloc((void**)&ctx->d_cell_items, (cell_items.size() + 1) * sizeof(uint16_t)));
-    ctx->cell_items_cap = cell_items.size() + 1;
+    CK(cudaMalloc((void**)&ctx->d_cell_items, (cell_items.size() + 8) * sizeof(uint16_t)));
+    ctx->cell_items_cap = cell_items.size() + 8;
   }
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaMemcpy(ctx->d_hot, hot.data(), hot.size() * sizeof(ObsHot), cudaMemcpyHostToDevice));
@@ -659,7 +667,7 @@ int clrrt_propagate_batch_ex(clrrt_ctx* ctx, const int32_t* parent, const double
   job.cand = b.d_parent; job.count = nullptr; job.cand_stride = 1; job.sample_xy = b.d_samples;
   job.parents = ctx->tree; job.out_records = b.d_out; job.traj = traj ? b.d_traj : nullptr; job.traj_stride = traj_stride;
   job.ref_out = ref_xyv ? b.d_ref : nullptr; job.ref_stride = ref_stride;
-  job.counters = ctx->d_counters; job.refill_min = ctx->refill_min;
+  job.counters = ctx->d_counters; job.refill_min = ctx->refill_min; job.phase_clk = ctx->d_counters + 8;
   if (!l0.empty()) {
     job.n_items = (int)l0.size(); job.item_list = b.d_list0; job.head = ctx->d_ints + 0;
     if ((rc = launch_rollout<false>(ctx, job, job.n_items))) return rc;
@@ -708,7 +716,7 @@ int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint
   job.cand_stride = CLRRT_SORT_LIMIT; job.sample_xy = d_sample_xy; job.parents = ctx->tree;
   job.best_rank = ctx->d_best; job.res_code = ctx->d_res_code; job.res_steps = ctx->d_res_steps;
   job.out_nodes = ctx->stage; job.out_offset = 0; job.out_valid = ctx->d_valid;
-  job.counters = nullptr; job.refill_min = ctx->refill_min;
+  job.counters = nullptr; job.refill_min = ctx->refill_min; job.phase_clk = ctx->d_counters + 8;
   ref_end_kernel<<<(job.n_items + 255) / 256, 256, 0, st>>>(K, CLRRT_SORT_LIMIT, ctx->d_cand, CLRRT_SORT_LIMIT, ctx->d_count,
                                                           d_sample_xy, nullptr, job.n_items, ctx->tree, ctx->d_ref_end);
   CK(cudaGetLastError());
@@ -728,7 +736,7 @@ int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint
     g.n_items = K; g.n_items_dev = ctx->d_ints + 2; g.n_samples = K; g.n_ranks = 1;
     g.head = ctx->d_ints + 1; g.item_list = ctx->d_gb_list; g.parent_slot = ctx->d_slot; g.parents = ctx->stage;
     g.out_nodes = ctx->stage; g.out_offset = K * CLRRT_SORT_LIMIT; g.out_valid = ctx->d_valid + K;
-    g.counters = ctx->d_counters; g.refill_min = ctx->refill_min;
+    g.counters = ctx->d_counters; g.refill_min = ctx->refill_min; g.phase_clk = ctx->d_counters + 8;
     if ((rc = launch_rollout<true>(ctx, g, K))) return rc;
   }
   CK(cudaEventRecord(ctx->ev[3], st));
@@ -819,6 +827,15 @@ int clrrt_set_tuning(clrrt_ctx* ctx, int refill_min, int blocks_per_sm) {
 int clrrt_set_grid_cell(clrrt_ctx* ctx, double metres) {
   if (!ctx || !(metres >= 0.05) || metres > 1000.0) return CLRRT_ERR_ARG;
   ctx->grid_cell = metres;  // takes effect at the next clrrt_set_obstacles
+  return CLRRT_OK;
+}
+
+int clrrt_debug_phase_clocks(clrrt_ctx* ctx, unsigned long long out[8], int reset) {
+  if (!ctx || !out) return CLRRT_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(out, ctx->d_counters + 8, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) CK(cudaMemset(ctx->d_counters + 8, 0, 8 * sizeof(unsigned long long)));
   return CLRRT_OK;
 }
 

@@ -54,14 +54,16 @@ struct __align__(16) ObsCold {  // read only when the vehicle's own axes did not
 // Broad-phase record (verdict-only mode, see rollout.cuh): bounding circle of a static obstacle.  The centre is
 // stored RELATIVE to the grid origin (subtracted in double on the host) so that float keeps ~1e-4 m over any scene.
 struct __align__(16) ObsBound {
-  float cx, cy, rr, pad;  // rr = half diagonal of the obstacle box + margin
+  float cx, cy, rr, ohh;   // rr = half diagonal of the obstacle box + margin; ohh/ohw = half extents along / across
+  float oc, os, ohw, pad;  // the obstacle's heading (oc, os) = (cosf, sinf) of it
 };
 // Moving obstacles: centre = c + vel*t with t = x[6] of the lane, so vertices are rebuilt per step from
 // host-computed float half-extent products (the float operation order of setVertices is preserved).
 struct __align__(16) ObsMoving {
   double cx, cy, vx, vy;
   float ch, sw, sh, cw;  // cosf(o)*(h/2), sinf(o)*(w/2), sinf(o)*(h/2), cosf(o)*(w/2)
-  float R2, pad[3];      // broad phase: pad[0] = rr = half diagonal + margin (+ slack for the float prediction); R2 unused
+  float rr, ohh, pad0, pad1;  // broad phase: rr = half diagonal + margin (+ slack for the float prediction), half length
+  float oc, os, ohw, pad2;    //              heading (cosf, sinf), half width — same layout as ObsBound's second half
 };
 
 // ---- parameters in constant memory -----------------------------------------------------------------------
