@@ -44,7 +44,10 @@ struct clrrt_ctx {
   int32_t* d_cell_start = nullptr;   // broad-phase grid (CSR): [cells + 1]
   uint16_t* d_cell_items = nullptr;
   size_t cell_start_cap = 0, cell_items_cap = 0;
+  uint4* d_pose_cells = nullptr;     // pose grid, built on the device by build_pose_grid_kernel
+  size_t pose_cap = 0;
   double grid_cell = 1.0;            // requested cell size in metres (clrrt_set_grid_cell)
+  bool pose_enabled = true;          // clrrt_set_grid_cell with a negative size disables the pose grid (tests)
   ObsCold* d_cold = nullptr;
   ObsMoving* d_mov = nullptr;
   int obs_cap = 0;
@@ -121,7 +124,7 @@ void fill_dev_params(clrrt_ctx* ctx) {
   memset(&d, 0, sizeof d);
   d.n_static = keep.n_static; d.n_moving = keep.n_moving; d.static_in_smem = keep.static_in_smem;
   d.grid_nx = keep.grid_nx; d.grid_ny = keep.grid_ny; d.grid_inv_cell = keep.grid_inv_cell;
-  d.grid_ox = keep.grid_ox; d.grid_oy = keep.grid_oy;
+  d.grid_ox = keep.grid_ox; d.grid_oy = keep.grid_oy; d.pose_sub = keep.pose_sub; d.pose_nh = keep.pose_nh;
   d.dmax = p.veh.dmax; d.ddmax = p.veh.ddmax; d.inv_Td = 1 / p.veh.Td; d.inv_Ta = 1 / p.veh.Ta;
   d.amin = p.veh.amin; d.amax = p.veh.amax; d.L = p.veh.L; d.Vch = p.veh.Vch; d.Kus = p.veh.Kus;
   d.sim_dt = p.sim_dt; d.mindla = p.ctrl_mindla; d.tla = p.ctrl_tla;
@@ -191,9 +194,9 @@ int configure_launch(clrrt_ctx* ctx) {
 
 template <typename R, bool GB> int launch_rollout_t(clrrt_ctx* ctx, const RolloutJob& job, int blocks) {
   if (ctx->dprm.exact_dist)
-    rollout_kernel<R, GB, true><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_cell_start, ctx->d_cell_items);
+    rollout_kernel<R, GB, true><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells);
   else
-    rollout_kernel<R, GB, false><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_cell_start, ctx->d_cell_items);
+    rollout_kernel<R, GB, false><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells);
   CK(cudaGetLastError());
   return CLRRT_OK;
 }
@@ -295,7 +298,7 @@ int clrrt_destroy(clrrt_ctx* ctx) {
   if (!ctx) return CLRRT_ERR_ARG;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  void* ptrs[] = {ctx->tree_mem, ctx->stage_mem, ctx->d_cell_start, ctx->d_cell_items, ctx->d_bnd, ctx->d_hot, ctx->d_best, ctx->d_res_code, ctx->d_res_steps, ctx->d_slot, ctx->d_ref_end, ctx->d_cold, ctx->d_mov, ctx->d_samples, ctx->d_heur,
+  void* ptrs[] = {ctx->tree_mem, ctx->stage_mem, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells, ctx->d_bnd, ctx->d_hot, ctx->d_best, ctx->d_res_code, ctx->d_res_steps, ctx->d_slot, ctx->d_ref_end, ctx->d_cold, ctx->d_mov, ctx->d_samples, ctx->d_heur,
                   ctx->d_cand, ctx->d_key, ctx->d_count, ctx->d_valid, ctx->d_gb_list, ctx->d_ints, ctx->d_block_sums,
                   ctx->d_records, ctx->d_counters, ctx->batch.d_parent, ctx->batch.d_list0, ctx->batch.d_list1,
                   ctx->batch.d_samples, ctx->batch.d_out, ctx->batch.d_traj, ctx->batch.d_ref};
@@ -481,6 +484,32 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
   ctx->dprm.n_moving = (int)mov.size();
   ctx->dprm.grid_nx = gnx; ctx->dprm.grid_ny = gny; ctx->dprm.grid_inv_cell = (float)(1.0 / cell);
   ctx->dprm.grid_ox = gox; ctx->dprm.grid_oy = goy;
+  // ---- pose grid: 2 x 2 sub-cells per position cell, 32 heading bins over pi (16 B per pose cell) ------------------
+  ctx->dprm.pose_sub = 1; ctx->dprm.pose_nh = 0;
+  if (ns > 0 && ctx->pose_enabled) {
+    const int nh = 32;
+    int sub = 2;
+    if ((double)gnx * gny * sub * sub * nh > 2.0e6) sub = 1;
+    const size_t cells = (size_t)gnx * gny * sub * sub * nh;
+    if ((double)cells <= 2.0e6) {
+      if (cells > ctx->pose_cap) {
+        if (ctx->d_pose_cells) cudaFree(ctx->d_pose_cells);
+        ctx->d_pose_cells = nullptr;
+        CK(cudaMalloc((void**)&ctx->d_pose_cells, cells * sizeof(uint4)));
+        ctx->pose_cap = cells;
+      }
+      const double cell_f = cell / sub, dth = M_PI / nh;
+      // farthest displacement of a point of the vehicle box when the pose moves inside a cell: half diagonal of the
+      // position cell + chord of the half heading bin at the box's half diagonal (+ 1 cm / 1 mrad for the float lookup)
+      const float infl = (float)(cell_f * M_SQRT1_2 + 0.01 + 2.0 * vreach * std::sin((dth / 2 + 1e-3) / 2));
+      build_pose_grid_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(
+          ctx->d_bnd, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells, ns, gnx, gny, sub, nh, (float)cell_f, infl,
+          ctx->dprm.veh_hh, ctx->dprm.veh_hw);
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(ctx->stream));
+      ctx->dprm.pose_sub = sub; ctx->dprm.pose_nh = nh;
+    }
+  }
   // the broad-phase table is staged in shared memory when it leaves room for the other resident blocks
   ctx->dprm.static_in_smem = (ns > 0 && obstacle_table_bytes(ns) <= 48 * 1024) ? 1 : 0;
   int rc = configure_launch(ctx);
@@ -825,8 +854,9 @@ int clrrt_set_tuning(clrrt_ctx* ctx, int refill_min, int blocks_per_sm) {
 }
 
 int clrrt_set_grid_cell(clrrt_ctx* ctx, double metres) {
-  if (!ctx || !(metres >= 0.05) || metres > 1000.0) return CLRRT_ERR_ARG;
-  ctx->grid_cell = metres;  // takes effect at the next clrrt_set_obstacles
+  if (!ctx || !(std::fabs(metres) >= 0.05) || std::fabs(metres) > 1000.0) return CLRRT_ERR_ARG;
+  ctx->grid_cell = std::fabs(metres);  // takes effect at the next clrrt_set_obstacles
+  ctx->pose_enabled = metres > 0;      // negative: position grid only (the fallback path), for tests
   return CLRRT_OK;
 }
 

@@ -89,6 +89,8 @@ struct DevParams {
   int32_t grid_nx, grid_ny;
   float grid_inv_cell;
   double grid_ox, grid_oy;
+  // pose grid (x, y, heading mod pi), pose_sub x pose_sub cells per position-grid cell; pose_nh == 0: not built
+  int32_t pose_sub, pose_nh;
   int32_t exact_dist;    // 1: return the reference's pseudo-distance (needed when W[2] != 0); 0: verdict only
   float veh_reach;       // half diagonal of the vehicle box (broad phase)
 };

@@ -185,8 +185,9 @@ int clrrt_get_device(const clrrt_ctx* ctx);
 /* Launch tuning of the rollout kernel: refill_min = idle lanes a warp accumulates before it fetches new work
  * (default 8; 1 = refill immediately); blocks_per_sm = resident blocks of the persistent grid (0 = occupancy maximum). */
 int clrrt_set_tuning(clrrt_ctx* ctx, int refill_min, int blocks_per_sm);
-/* Broad-phase grid of the collision check: cell size in metres (default 1), applied at the next clrrt_set_obstacles;
- * results do not depend on it. */
+/* Broad-phase grids of the collision check: cell size of the position grid in metres (default 1; the pose grid uses
+ * half of it), applied at the next clrrt_set_obstacles; a negative size disables the pose grid, leaving the position
+ * grid path only.  Results do not depend on it. */
 int clrrt_set_grid_cell(clrrt_ctx* ctx, double metres);
 
 #ifdef __cplusplus

@@ -192,7 +192,7 @@ def test_full_size_properties(clrrt, planner):
     planner.set_grid_cell(0.3)
     planner.set_obstacles(boxes)
     c = planner.propagate_batch(par, s)
-    planner.set_grid_cell(7.0)   # cells with more than 64 listed obstacles: the chunked broad phase
+    planner.set_grid_cell(-7.0)  # position grid only, cells with more than 64 listed obstacles: the chunked broad phase
     planner.set_obstacles(boxes)
     d = planner.propagate_batch(par, s)
     planner.set_tuning(refill_min=8, blocks_per_sm=0)
