@@ -19,7 +19,8 @@ namespace {
 
 struct RolloutScratch {
   int cap = 0;
-  int32_t *d_parent = nullptr, *d_list0 = nullptr, *d_list1 = nullptr;
+  int32_t* d_parent = nullptr;
+  uint8_t* d_gb = nullptr;
   double* d_samples = nullptr;
   clrrt_rollout* d_out = nullptr;
   double* d_traj = nullptr;
@@ -54,7 +55,10 @@ struct clrrt_ctx {
   // round scratch
   double* d_samples = nullptr;
   uint8_t* d_heur = nullptr;
-  int32_t *d_cand = nullptr, *d_count = nullptr, *d_valid = nullptr, *d_gb_list = nullptr;
+  int32_t *d_cand = nullptr, *d_count = nullptr, *d_valid = nullptr;
+  int32_t *d_order = nullptr, *d_hist = nullptr;  // launch order of the (sample, rank) pairs; (rank, length bucket) histogram
+  uint32_t* d_done = nullptr;
+  uint8_t* d_bucket = nullptr;
   int32_t *d_best = nullptr, *d_slot = nullptr;
   uint8_t* d_res_code = nullptr;
   uint16_t* d_res_steps = nullptr;
@@ -170,20 +174,12 @@ int ensure_params(clrrt_ctx* ctx) {
 
 template <typename R> int configure_launch_t(clrrt_ctx* ctx) {
   const int sm = (int)ctx->smem_bytes;
-  CK(cudaFuncSetAttribute(rollout_kernel<R, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  CK(cudaFuncSetAttribute(rollout_kernel<R, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  CK(cudaFuncSetAttribute(rollout_kernel<R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  CK(cudaFuncSetAttribute(rollout_kernel<R, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  int b0 = 1, b1 = 1;
-  if (ctx->dprm.exact_dist) {
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rollout_kernel<R, false, true>, ROLLOUT_THREADS, ctx->smem_bytes));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, rollout_kernel<R, true, true>, ROLLOUT_THREADS, ctx->smem_bytes));
-  } else {
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rollout_kernel<R, false, false>, ROLLOUT_THREADS, ctx->smem_bytes));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, rollout_kernel<R, true, false>, ROLLOUT_THREADS, ctx->smem_bytes));
-  }
+  CK(cudaFuncSetAttribute(rollout_kernel<R, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(rollout_kernel<R, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  int b0 = 1;
+  if (ctx->dprm.exact_dist) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rollout_kernel<R, 2, true>, ROLLOUT_THREADS, ctx->smem_bytes));
+  else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rollout_kernel<R, 2, false>, ROLLOUT_THREADS, ctx->smem_bytes));
   ctx->blocks_per_sm_main = std::max(1, b0);
-  ctx->blocks_per_sm_gb = std::max(1, b1);
   return CLRRT_OK;
 }
 
@@ -192,23 +188,24 @@ int configure_launch(clrrt_ctx* ctx) {
   return ctx->prm.fp32 ? configure_launch_t<float>(ctx) : configure_launch_t<double>(ctx);
 }
 
-template <typename R, bool GB> int launch_rollout_t(clrrt_ctx* ctx, const RolloutJob& job, int blocks) {
+// One kernel for everything: plain and goal-biased rollouts are told apart per lane at run time (GBM = 2).
+template <typename R> int launch_rollout_t(clrrt_ctx* ctx, const RolloutJob& job, int blocks) {
   if (ctx->dprm.exact_dist)
-    rollout_kernel<R, GB, true><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells);
+    rollout_kernel<R, 2, true><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells);
   else
-    rollout_kernel<R, GB, false><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells);
+    rollout_kernel<R, 2, false><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells);
   CK(cudaGetLastError());
   return CLRRT_OK;
 }
 
-template <bool GB> int launch_rollout(clrrt_ctx* ctx, const RolloutJob& job, int n_items_hint) {
-  int per_sm = GB ? ctx->blocks_per_sm_gb : ctx->blocks_per_sm_main;
+int launch_rollout(clrrt_ctx* ctx, const RolloutJob& job, int n_items_hint) {
+  int per_sm = ctx->blocks_per_sm_main;
   if (ctx->blocks_override > 0) per_sm = std::min(per_sm, ctx->blocks_override);
   const int lanes_per_block = ROLLOUT_THREADS;
   int blocks = ctx->num_sms * per_sm;  // persistent grid: a multiple of the SM count
   const int needed = (n_items_hint + lanes_per_block - 1) / lanes_per_block;
   if (needed < blocks) blocks = std::max(1, needed);
-  return ctx->prm.fp32 ? launch_rollout_t<float, GB>(ctx, job, blocks) : launch_rollout_t<double, GB>(ctx, job, blocks);
+  return ctx->prm.fp32 ? launch_rollout_t<float>(ctx, job, blocks) : launch_rollout_t<double>(ctx, job, blocks);
 }
 
 }  // namespace
@@ -270,7 +267,10 @@ int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_r
   ok &= mal((void**)&ctx->d_key, K * CLRRT_SORT_LIMIT * sizeof(float));
   ok &= mal((void**)&ctx->d_count, K * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_valid, 2 * K * sizeof(int32_t));
-  ok &= mal((void**)&ctx->d_gb_list, K * sizeof(int32_t));
+  ok &= mal((void**)&ctx->d_order, K * CLRRT_SORT_LIMIT * sizeof(int32_t));
+  ok &= mal((void**)&ctx->d_hist, 1024 * sizeof(int32_t));
+  ok &= mal((void**)&ctx->d_done, K * sizeof(uint32_t));
+  ok &= mal((void**)&ctx->d_bucket, K * CLRRT_SORT_LIMIT);
   ok &= mal((void**)&ctx->d_best, K * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_slot, K * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_res_code, K * CLRRT_SORT_LIMIT);
@@ -299,8 +299,8 @@ int clrrt_destroy(clrrt_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->tree_mem, ctx->stage_mem, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells, ctx->d_bnd, ctx->d_hot, ctx->d_best, ctx->d_res_code, ctx->d_res_steps, ctx->d_slot, ctx->d_ref_end, ctx->d_cold, ctx->d_mov, ctx->d_samples, ctx->d_heur,
-                  ctx->d_cand, ctx->d_key, ctx->d_count, ctx->d_valid, ctx->d_gb_list, ctx->d_ints, ctx->d_block_sums,
-                  ctx->d_records, ctx->d_counters, ctx->batch.d_parent, ctx->batch.d_list0, ctx->batch.d_list1,
+                  ctx->d_cand, ctx->d_key, ctx->d_count, ctx->d_valid, ctx->d_order, ctx->d_hist, ctx->d_done, ctx->d_bucket, ctx->d_ints, ctx->d_block_sums,
+                  ctx->d_records, ctx->d_counters, ctx->batch.d_parent, ctx->batch.d_gb,
                   ctx->batch.d_samples, ctx->batch.d_out, ctx->batch.d_traj, ctx->batch.d_ref};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->h_ints) cudaFreeHost(ctx->h_ints);
@@ -660,11 +660,10 @@ int clrrt_propagate_batch_ex(clrrt_ctx* ctx, const int32_t* parent, const double
   if (rc) return rc;
   RolloutScratch& b = ctx->batch;
   if (M > b.cap) {
-    void* ptrs[] = {b.d_parent, b.d_list0, b.d_list1, b.d_samples, b.d_out};
+    void* ptrs[] = {b.d_parent, b.d_gb, b.d_samples, b.d_out};
     for (void* p : ptrs) if (p) cudaFree(p);
     CK(cudaMalloc((void**)&b.d_parent, (size_t)M * 4));
-    CK(cudaMalloc((void**)&b.d_list0, (size_t)M * 4));
-    CK(cudaMalloc((void**)&b.d_list1, (size_t)M * 4));
+    CK(cudaMalloc((void**)&b.d_gb, (size_t)M));
     CK(cudaMalloc((void**)&b.d_samples, (size_t)M * 16));
     CK(cudaMalloc((void**)&b.d_out, (size_t)M * sizeof(clrrt_rollout)));
     b.cap = M;
@@ -681,12 +680,11 @@ int clrrt_propagate_batch_ex(clrrt_ctx* ctx, const int32_t* parent, const double
     CK(cudaMalloc((void**)&b.d_ref, ref_elems * 8));
     b.ref_cap = ref_elems;
   }
-  std::vector<int32_t> l0, l1;
-  for (int i = 0; i < M; i++) ((goal_biased && goal_biased[i]) ? l1 : l0).push_back(i);
+  std::vector<uint8_t> gbf((size_t)M, 0);
+  if (goal_biased) for (int i = 0; i < M; i++) gbf[i] = goal_biased[i] ? 1 : 0;
   CK(cudaMemcpyAsync(b.d_parent, parent, (size_t)M * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(b.d_samples, sample_xy, (size_t)M * 16, cudaMemcpyHostToDevice, ctx->stream));
-  if (!l0.empty()) CK(cudaMemcpyAsync(b.d_list0, l0.data(), l0.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-  if (!l1.empty()) CK(cudaMemcpyAsync(b.d_list1, l1.data(), l1.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(b.d_gb, gbf.data(), (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(ctx->d_ints, 0, 4 * sizeof(int32_t), ctx->stream));
   if (traj) CK(cudaMemsetAsync(b.d_traj, 0, traj_elems * 8, ctx->stream));
   if (ref_xyv) CK(cudaMemsetAsync(b.d_ref, 0, ref_elems * 8, ctx->stream));
@@ -697,14 +695,8 @@ int clrrt_propagate_batch_ex(clrrt_ctx* ctx, const int32_t* parent, const double
   job.parents = ctx->tree; job.out_records = b.d_out; job.traj = traj ? b.d_traj : nullptr; job.traj_stride = traj_stride;
   job.ref_out = ref_xyv ? b.d_ref : nullptr; job.ref_stride = ref_stride;
   job.counters = ctx->d_counters; job.refill_min = ctx->refill_min; job.phase_clk = ctx->d_counters + 8;
-  if (!l0.empty()) {
-    job.n_items = (int)l0.size(); job.item_list = b.d_list0; job.head = ctx->d_ints + 0;
-    if ((rc = launch_rollout<false>(ctx, job, job.n_items))) return rc;
-  }
-  if (!l1.empty()) {
-    job.n_items = (int)l1.size(); job.item_list = b.d_list1; job.head = ctx->d_ints + 1;
-    if ((rc = launch_rollout<true>(ctx, job, job.n_items))) return rc;
-  }
+  job.n_items = M; job.gb_flags = b.d_gb; job.head = ctx->d_ints + 0;
+  if ((rc = launch_rollout(ctx, job, M))) return rc;
   CK(cudaMemcpyAsync(out, b.d_out, (size_t)M * sizeof(clrrt_rollout), cudaMemcpyDeviceToHost, ctx->stream));
   if (traj) CK(cudaMemcpyAsync(traj, b.d_traj, traj_elems * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (ref_xyv) CK(cudaMemcpyAsync(ref_xyv, b.d_ref, ref_elems * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -734,40 +726,37 @@ int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint
   // 1. candidate parents
   if ((rc = nearest_dev(ctx, d_sample_xy, d_heuristic, K, ctx->d_cand, nullptr, ctx->d_count))) return rc;
   CK(cudaEventRecord(ctx->ev[1], st));
-  // 2. rollouts of all candidates, rank-major, with early skip: equivalent to trying them in order until the first success
+  // 2. rollouts of all candidates, rank-major (longest references first within a rank), with early skip: equivalent to
+  //    trying them in order until the first success; the goal-biased rollout of a sample's winner continues on the lane
+  //    that resolved the sample (rollout.cuh)
+  const int n_pairs = K * CLRRT_SORT_LIMIT;
   CK(cudaMemsetAsync(ctx->d_ints, 0, 4 * sizeof(int32_t), st));
   CK(cudaMemsetAsync(ctx->d_best, 0x7f, (size_t)K * sizeof(int32_t), st));
+  CK(cudaMemsetAsync(ctx->d_done, 0, (size_t)K * sizeof(uint32_t), st));
+  CK(cudaMemsetAsync(ctx->d_valid + K, 0, (size_t)K * sizeof(int32_t), st));
+  CK(cudaMemsetAsync(ctx->d_hist, 0, 1024 * sizeof(int32_t), st));
   CK(cudaMemcpyAsync(ctx->h_counters + 8, ctx->d_counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  ref_end_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(K, CLRRT_SORT_LIMIT, ctx->d_cand, CLRRT_SORT_LIMIT, ctx->d_count, d_sample_xy,
+                                                       n_pairs, ctx->tree, ctx->d_ref_end, ctx->d_bucket, ctx->d_hist);
+  order_scan_kernel<<<1, 1024, 0, st>>>(ctx->d_hist, CLRRT_SORT_LIMIT * ORDER_BUCKETS, ctx->d_ints + 2);
+  order_scatter_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(K, CLRRT_SORT_LIMIT, ctx->d_count, ctx->d_bucket, ctx->d_hist, ctx->d_order);
+  CK(cudaGetLastError());
   RolloutJob job;
   memset(&job, 0, sizeof job);
-  job.n_samples = K; job.n_ranks = CLRRT_SORT_LIMIT; job.n_items = K * CLRRT_SORT_LIMIT;
-  job.head = ctx->d_ints + 0; job.cand = ctx->d_cand; job.count = ctx->d_count;
-  job.cand_stride = CLRRT_SORT_LIMIT; job.sample_xy = d_sample_xy; job.parents = ctx->tree;
-  job.best_rank = ctx->d_best; job.res_code = ctx->d_res_code; job.res_steps = ctx->d_res_steps;
-  job.out_nodes = ctx->stage; job.out_offset = 0; job.out_valid = ctx->d_valid;
-  job.counters = nullptr; job.refill_min = ctx->refill_min; job.phase_clk = ctx->d_counters + 8;
-  ref_end_kernel<<<(job.n_items + 255) / 256, 256, 0, st>>>(K, CLRRT_SORT_LIMIT, ctx->d_cand, CLRRT_SORT_LIMIT, ctx->d_count,
-                                                          d_sample_xy, nullptr, job.n_items, ctx->tree, ctx->d_ref_end);
-  CK(cudaGetLastError());
-  job.ref_end = ctx->d_ref_end;
-  if ((rc = launch_rollout<false>(ctx, job, job.n_items))) return rc;
+  job.n_samples = K; job.n_ranks = CLRRT_SORT_LIMIT; job.n_items = n_pairs; job.n_items_dev = ctx->d_ints + 2;
+  job.head = ctx->d_ints + 0; job.cand = ctx->d_cand; job.count = ctx->d_count; job.order = ctx->d_order;
+  job.cand_stride = CLRRT_SORT_LIMIT; job.sample_xy = d_sample_xy; job.parents = ctx->tree; job.ref_end = ctx->d_ref_end;
+  job.best_rank = ctx->d_best; job.done_mask = ctx->d_done; job.res_code = ctx->d_res_code; job.res_steps = ctx->d_res_steps;
+  job.out_nodes = ctx->stage; job.out_valid = ctx->d_valid;
+  job.counters = ctx->d_counters; job.refill_min = ctx->refill_min; job.phase_clk = ctx->d_counters + 8;
+  if ((rc = launch_rollout(ctx, job, n_pairs))) return rc;
+  CK(cudaEventRecord(ctx->ev[2], st));
   SelectArgs sa;
   sa.K = K; sa.n_ranks = CLRRT_SORT_LIMIT; sa.count = ctx->d_count; sa.best_rank = ctx->d_best;
-  sa.res_code = ctx->d_res_code; sa.res_steps = ctx->d_res_steps; sa.stage = ctx->stage; sa.valid = ctx->d_valid;
-  sa.slot = ctx->d_slot; sa.gb_list = ctx->d_gb_list; sa.gb_count = ctx->d_ints + 2; sa.counters = ctx->d_counters;
+  sa.res_code = ctx->d_res_code; sa.res_steps = ctx->d_res_steps; sa.valid = ctx->d_valid;
+  sa.slot = ctx->d_slot; sa.counters = ctx->d_counters;
   select_kernel<<<(K + 255) / 256, 256, 0, st>>>(sa);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(ctx->ev[2], st));
-  // 3. goal-biased rollout from every node just accepted that passes feasibleGoalBias (item count stays on the device)
-  {
-    RolloutJob g;
-    memset(&g, 0, sizeof g);
-    g.n_items = K; g.n_items_dev = ctx->d_ints + 2; g.n_samples = K; g.n_ranks = 1;
-    g.head = ctx->d_ints + 1; g.item_list = ctx->d_gb_list; g.parent_slot = ctx->d_slot; g.parents = ctx->stage;
-    g.out_nodes = ctx->stage; g.out_offset = K * CLRRT_SORT_LIMIT; g.out_valid = ctx->d_valid + K;
-    g.counters = ctx->d_counters; g.refill_min = ctx->refill_min; g.phase_clk = ctx->d_counters + 8;
-    if ((rc = launch_rollout<true>(ctx, g, K))) return rc;
-  }
   CK(cudaEventRecord(ctx->ev[3], st));
   // 4. compaction in sample order -> records -> append
   const int nblocks = (K + SCAN_THREADS - 1) / SCAN_THREADS;
