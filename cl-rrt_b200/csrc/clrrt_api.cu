@@ -279,11 +279,11 @@ int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_r
   ok &= mal((void**)&ctx->d_ints, 16 * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_block_sums, ((K + SCAN_THREADS - 1) / SCAN_THREADS + 1) * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_records, 2 * K * sizeof(NodeRecord));
-  ok &= mal((void**)&ctx->d_counters, 16 * sizeof(unsigned long long));
+  ok &= mal((void**)&ctx->d_counters, 32 * sizeof(unsigned long long));
   ok &= cudaMallocHost((void**)&ctx->h_ints, 16 * sizeof(int32_t)) == cudaSuccess;
   ok &= cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(unsigned long long)) == cudaSuccess;
   if (!ok) { ctx->err = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()); return fail(CLRRT_ERR_CUDA); }
-  cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), ctx->stream);
+  cudaMemsetAsync(ctx->d_counters, 0, 32 * sizeof(unsigned long long), ctx->stream);
   cudaMemsetAsync(ctx->d_ints, 0, 16 * sizeof(int32_t), ctx->stream);
   for (auto& e : ctx->ev) cudaEventCreate(&e);
   fill_dev_params(ctx);
@@ -849,12 +849,12 @@ int clrrt_set_grid_cell(clrrt_ctx* ctx, double metres) {
   return CLRRT_OK;
 }
 
-int clrrt_debug_phase_clocks(clrrt_ctx* ctx, unsigned long long out[8], int reset) {
+int clrrt_debug_phase_clocks(clrrt_ctx* ctx, unsigned long long out[16], int reset) {
   if (!ctx || !out) return CLRRT_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
-  CK(cudaMemcpy(out, ctx->d_counters + 8, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  if (reset) CK(cudaMemset(ctx->d_counters + 8, 0, 8 * sizeof(unsigned long long)));
+  CK(cudaMemcpy(out, ctx->d_counters + 8, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) CK(cudaMemset(ctx->d_counters + 8, 0, 16 * sizeof(unsigned long long)));
   return CLRRT_OK;
 }
 

@@ -4,9 +4,9 @@
 // feasibleNode (:271-289).  The reference computes a key for EVERY node, fully sorts, then walks the sorted
 // list testing feasibility until 10 nodes are found.  The same list is produced here without a sort:
 //   block = 8 warps = 8 samples; the node fields are staged tile by tile in shared memory and shared by the
-//   8 samples; lanes stride over the tile; infeasible nodes are dropped BEFORE their key is computed (the
-//   result is the same: the reference also skips them, after sorting); each lane keeps its own sorted top-10
-//   in registers; the 32 lists are merged with warp shuffles.  Ties between equal keys go to the lower node id.
+//   8 samples; lanes stride over the tile; nodes that cannot enter the list (distance bound) and infeasible nodes are
+//   dropped BEFORE their key is computed (the result is the same: the reference also skips infeasible nodes, after
+//   sorting); the warp keeps one sorted top-10 in registers.  Ties between equal keys go to the lower node id.
 // Arithmetic types follow dubinsDistance exactly: the whole metric is float (double enters only through
 // S - N.state and the M_PI terms); feasibility is double.
 #pragma once
@@ -80,21 +80,29 @@ __device__ __forceinline__ bool feasible_node(double sx, double sy, double rbx, 
   return !(sqrt(l2) < feas_len);
 }
 
+// The running top-10 of a sample lives in registers of lanes 0..9 of its warp (lane r = r-th best so far), ordered by
+// (key, node id).  Its last entry T bounds the search: the Dubins key is never below the Euclidean distance from
+// the node to the sample (checked over the whole float domain of dubinsDistance: key >= (1 - 3e-6) d outside the turning
+// circles, key >= 1.58 d inside), so a node with 0.999 d > T (0.999 d + costE > T for the optimise key) cannot enter
+// the list and is dropped before its feasibility or its key is evaluated.  Three compaction stages keep the expensive
+// parts on full warps: distance bound (all nodes of a tile) -> feasibility (survivors) -> key (feasible survivors).
 __global__ void __launch_bounds__(NEAREST_THREADS) nearest_topk_kernel(const NearestArgs a) {
   __shared__ double s_nx[NEAREST_TILE], s_ny[NEAREST_TILE], s_rbx[NEAREST_TILE], s_rby[NEAREST_TILE];
   __shared__ double s_dpx[NEAREST_TILE], s_dpy[NEAREST_TILE], s_ang[NEAREST_TILE];
   __shared__ float s_ca[NEAREST_TILE], s_sa[NEAREST_TILE], s_ce[NEAREST_TILE];
   __shared__ uint16_t s_idx[NEAREST_WARPS][NEAREST_TILE];
+  __shared__ uint16_t s_idx2[NEAREST_WARPS][NEAREST_TILE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
   const int j = blockIdx.x * NEAREST_WARPS + warp;
   const bool live = j < a.K;
   double sx = 0, sy = 0;
   bool optimize = false;
   if (live) { sx = a.sample_xy[2 * j]; sy = a.sample_xy[2 * j + 1]; optimize = a.heuristic[j] != 0; }
-  float k[CLRRT_SORT_LIMIT];
-  int id[CLRRT_SORT_LIMIT];
-#pragma unroll
-  for (int r = 0; r < CLRRT_SORT_LIMIT; r++) { k[r] = INFINITY; id[r] = INT_MAX; }
+  float lk = INFINITY;  // entry `lane` of the list (lanes >= 10 stay at +inf / INT_MAX and never take part)
+  int lid = INT_MAX;
+  float T = INFINITY;   // key and id of the 10th entry (warp-uniform)
+  int Tid = INT_MAX;
 
   for (int base = 0; base < a.n_nodes; base += NEAREST_TILE) {
     const int n = min(NEAREST_TILE, a.n_nodes - base);
@@ -110,61 +118,76 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_topk_kernel(const Nea
     }
     __syncthreads();
     if (live) {
-      // pass 1: feasibility of the tile's nodes for this sample; feasible ones are compacted into a per-warp index
-      // list with ballot/popc, so that the (much more expensive) key evaluation below runs on full warps
-      int cnt = 0;
+      // stage 1: distance bound against T
+      int c1 = 0;
       for (int i0 = 0; i0 < n; i0 += 32) {
         const int i = i0 + lane;
-        const bool f = i < n && feasible_node(sx, sy, s_rbx[i], s_rby[i], s_dpx[i], s_dpy[i], s_ang[i], a.feas_len);
-        const unsigned m = __ballot_sync(FULL_MASK, f);
-        if (f) s_idx[warp][cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
-        cnt += __popc(m);
+        bool keep = false;
+        if (i < n) {
+          const float ex = (float)(sx - s_nx[i]), ey = (float)(sy - s_ny[i]);
+          const float lb = 0.999f * sqrtf(ex * ex + ey * ey) + (optimize ? s_ce[i] : 0.0f);
+          keep = !(lb > T);  // NaN bounds are kept
+        }
+        const unsigned m = __ballot_sync(FULL_MASK, keep);
+        if (keep) s_idx[warp][c1 + __popc(m & lt)] = (uint16_t)i;
+        c1 += __popc(m);
       }
       __syncwarp();
-      // pass 2: Dubins keys of the feasible nodes, per-lane sorted top-10 (a lane sees its nodes in increasing id order)
-      for (int q = lane; q < cnt; q += 32) {
-        const int i = s_idx[warp][q];
-        float key = dubins_key(sx, sy, s_nx[i], s_ny[i], s_ca[i], s_sa[i]);
-        if (optimize) key = s_ce[i] + key;  // rrtplanner.cpp:254
-        if (key < k[CLRRT_SORT_LIMIT - 1]) {
-          const int idx = base + i;
-          bool placed = false;
-#pragma unroll
-          for (int r = CLRRT_SORT_LIMIT - 1; r >= 0; r--) {
-            if (!placed) {
-              if (r > 0 && key < k[r - 1]) { k[r] = k[r - 1]; id[r] = id[r - 1]; }
-              else { k[r] = key; id[r] = idx; placed = true; }
-            }
+      // stage 2: feasibility of the survivors
+      int c2 = 0;
+      for (int q0 = 0; q0 < c1; q0 += 32) {
+        const int q = q0 + lane;
+        int i = 0;
+        bool f = false;
+        if (q < c1) {
+          i = s_idx[warp][q];
+          f = feasible_node(sx, sy, s_rbx[i], s_rby[i], s_dpx[i], s_dpy[i], s_ang[i], a.feas_len);
+        }
+        const unsigned m = __ballot_sync(FULL_MASK, f);
+        if (f) s_idx2[warp][c2 + __popc(m & lt)] = (uint16_t)i;
+        c2 += __popc(m);
+      }
+      __syncwarp();
+      // stage 3: Dubins keys of the feasible survivors (increasing node id) and insertion into the warp's list
+      for (int q0 = 0; q0 < c2; q0 += 32) {
+        const int q = q0 + lane;
+        float key = INFINITY;
+        int idx = INT_MAX;
+        if (q < c2) {
+          const int i = s_idx2[warp][q];
+          key = dubins_key(sx, sy, s_nx[i], s_ny[i], s_ca[i], s_sa[i]);
+          if (optimize) key = s_ce[i] + key;  // rrtplanner.cpp:254
+          idx = base + i;
+        }
+        unsigned want = __ballot_sync(FULL_MASK, key < T || (key == T && idx < Tid));
+        while (want) {
+          const int src = __ffs(want) - 1;
+          want &= want - 1;
+          const float nk = __shfl_sync(FULL_MASK, key, src);
+          const int nid = __shfl_sync(FULL_MASK, idx, src);
+          if (!(nk < T || (nk == T && nid < Tid))) continue;  // T moved since the ballot
+          // position = number of entries ordered before the new one; entries from there on move down one lane
+          const bool before = lk < nk || (lk == nk && lid < nid);
+          const int pos = __popc(__ballot_sync(FULL_MASK, before && lane < CLRRT_SORT_LIMIT));
+          const float uk = __shfl_up_sync(FULL_MASK, lk, 1);
+          const int uid = __shfl_up_sync(FULL_MASK, lid, 1);
+          if (lane < CLRRT_SORT_LIMIT) {
+            if (lane == pos) { lk = nk; lid = nid; }
+            else if (lane > pos) { lk = uk; lid = uid; }
           }
+          T = __shfl_sync(FULL_MASK, lk, CLRRT_SORT_LIMIT - 1);
+          Tid = __shfl_sync(FULL_MASK, lid, CLRRT_SORT_LIMIT - 1);
         }
       }
       __syncwarp();
     }
   }
   if (!live) return;
-  // merge the 32 sorted lists: 10 rounds of warp arg-min on (key, id)
-  int cnt = 0;
-#pragma unroll 1
-  for (int r = 0; r < CLRRT_SORT_LIMIT; r++) {
-    float hk = k[0];
-    int hid = id[0];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ok = __shfl_xor_sync(FULL_MASK, hk, o);
-      const int oid = __shfl_xor_sync(FULL_MASK, hid, o);
-      if (ok < hk || (ok == hk && oid < hid)) { hk = ok; hid = oid; }
-    }
-    if (id[0] == hid && hid != INT_MAX) {
-#pragma unroll
-      for (int q = 0; q < CLRRT_SORT_LIMIT - 1; q++) { k[q] = k[q + 1]; id[q] = id[q + 1]; }
-      k[CLRRT_SORT_LIMIT - 1] = INFINITY; id[CLRRT_SORT_LIMIT - 1] = INT_MAX;
-    }
-    const bool valid = hid != INT_MAX;
-    if (valid) cnt++;
-    if (lane == 0) {
-      a.cand[(size_t)j * CLRRT_SORT_LIMIT + r] = valid ? hid : -1;
-      if (a.key) a.key[(size_t)j * CLRRT_SORT_LIMIT + r] = valid ? hk : 0.0f;
-    }
+  const int cnt = __popc(__ballot_sync(FULL_MASK, lane < CLRRT_SORT_LIMIT && lid != INT_MAX));
+  if (lane < CLRRT_SORT_LIMIT) {
+    const bool valid = lid != INT_MAX;
+    a.cand[(size_t)j * CLRRT_SORT_LIMIT + lane] = valid ? lid : -1;
+    if (a.key) a.key[(size_t)j * CLRRT_SORT_LIMIT + lane] = valid ? lk : 0.0f;
   }
   if (lane == 0) a.count[j] = cnt;
 }

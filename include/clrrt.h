@@ -177,7 +177,7 @@ int clrrt_draw_samples(const double goal[4], int K, double* sample_xy, uint8_t* 
 int clrrt_set_defer_append(clrrt_ctx* ctx, int defer);
 /* Kernel-tuning aid: per-phase clock totals of the rollout kernels (refill, dynamics, collision, finish, warp steps),
  * non-zero only in builds compiled with -DCLRRT_PHASE_CLOCKS. */
-int clrrt_debug_phase_clocks(clrrt_ctx* ctx, unsigned long long out[8], int reset);
+int clrrt_debug_phase_clocks(clrrt_ctx* ctx, unsigned long long out[16], int reset);
 int clrrt_round_records(clrrt_ctx* ctx, void** d_records, int* n_records);
 int clrrt_append_records(clrrt_ctx* ctx, const void* d_records, const int32_t* counts, int world, int stride_records);
 
