@@ -45,34 +45,55 @@ def scene_c3_boxes():
     return o
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe): one nvidia-smi process
+    sampling every 100 ms from before the warm-up until after the last timed step; rows carry their own timestamps and
+    only those inside [mark_begin, mark_end] are summarised."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.proc, self.t0, self.t1 = None, None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def summary(self):
-        if not self.rows:
+        import datetime
+        if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        rows = []
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), f[3:7]))
+            except Exception:
+                continue
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi gave no samples"]}
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.05 <= r[0] <= (self.t1 or 1e18) + 0.05] or rows
+        sm = sorted(r[1] for r in inside)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+        reasons = [n for k, n in enumerate(names) if any(r[3][k].lower().startswith("active") for r in inside)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": inside[0][2], "reasons": reasons, "samples": len(inside),
+                "samples_total": len(rows)}
 
 
 def build_workload(pl, clrrt, rank, world):
@@ -92,6 +113,59 @@ def build_workload(pl, clrrt, rank, world):
     # every rank draws the global stream and keeps its contiguous shard
     gs, gh = clrrt.draw_samples(GOAL, K_ROUND * world, seed=2)
     return boxes, gs[rank * K_ROUND:(rank + 1) * K_ROUND].copy(), gh[rank * K_ROUND:(rank + 1) * K_ROUND].copy()
+
+
+C1_CAR = (0.0, 0.0, 0.0, 0.0, 0.0, 0.0)
+C1_GOAL = (50.0, 0.0, 0.0, 0.0)
+
+
+def scene_c1_boxes():
+    """10 static boxes, centre (8 + 4.7 i, +3 even / -3 odd), size_x 4, size_y 8."""
+    o = np.zeros((10, 7))
+    for i in range(10):
+        o[i] = [8 + 4.7 * i, 3.0 if i % 2 == 0 else -3.0, 0.0, 4.0, 8.0, 0.0, 0.0]
+    return o
+
+
+def query_200ms_ours(clrrt, device, K=4096, budget_ms=200.0):
+    """Second half of BASELINE.json's metric: tree nodes grown by one planMotion query with a 200 ms expansion budget
+    (config C1).  Samples are drawn on the host with the reference's expressions (rand() after srand(1)), K per round;
+    the wall clock covers drawing, the host->device copy and the round."""
+    pl = clrrt.Planner(device=device, tree_capacity=(1 << 20) + 2 * K, max_round=K)
+    pl.set_query(C1_CAR, C1_GOAL, VMAX)
+    pl.set_obstacles(scene_c1_boxes())
+    pl.tree_reset(clrrt.root_node(C1_CAR))
+    s, h = clrrt.draw_samples(C1_GOAL, K, seed=1)
+    pl.expand_round(s, h)  # warm-up (first launch, lazy module load), then start over
+    pl.tree_reset(clrrt.root_node(C1_CAR))
+    clrrt.draw_samples(C1_GOAL, 1, seed=1)
+    rounds = steps = rollouts = 0
+    t0 = time.perf_counter()
+    while (time.perf_counter() - t0) * 1e3 < budget_ms and pl.tree_size() < (1 << 20):
+        s, h = clrrt.draw_samples(C1_GOAL, K)
+        st = pl.expand_round(s, h)
+        rounds += 1
+        steps += st.sim_steps
+        rollouts += st.rollouts
+    wall = (time.perf_counter() - t0) * 1e3
+    nodes = pl.tree_size()
+    path = len(pl.best_path())
+    pl.close()
+    return {"nodes": int(nodes), "rounds": rounds, "samples_per_round": K, "sim_steps": int(steps), "rollouts": int(rollouts),
+            "wall_ms": wall, "budget_ms": budget_ms, "best_path_nodes": int(path),
+            "scene": "C1: straight road, goal 50 m ahead, 10 static boxes, Prius parameters"}
+
+
+def query_200ms_reference(kind, budget_ms=200.0):
+    """The reference's own loop (Timer(200) around expandTree, rrt/src/motionplanner.cpp:39-43) on one host core."""
+    from cpulib import CpuPlanner
+    cpu = CpuPlanner(kind)
+    cpu.set_obstacles(scene_c1_boxes())
+    cpu.srand(1)
+    cpu.tree_init(C1_CAR, C1_GOAL, VMAX)
+    nodes, it = cpu.expand_timed(budget_ms)
+    return {"nodes": int(nodes), "iterations": int(it), "budget_ms": budget_ms, "cores": 1,
+            "scene": "C1: straight road, goal 50 m ahead, 10 static boxes, Prius parameters"}
 
 
 def cpu_baseline_sample(boxes, tree_records, samples, heur, budget_s=12.0, kind=None):
@@ -175,6 +249,7 @@ def run_ours(args):
     d_heu = torch.from_numpy(heu).cuda()
     h_smp = torch.from_numpy(smp).pin_memory()
     h_heu = torch.from_numpy(heu).pin_memory()
+    np_smp, np_heu = h_smp.numpy(), h_heu.numpy()  # views of the pinned buffers
     if world > 1:
         from clrrt_b200.exchange import gather_records
         pl.set_defer_append(True)
@@ -198,9 +273,9 @@ def run_ours(args):
         if dev_inputs:
             st = pl.expand_round_dev(d_smp.data_ptr(), d_heu.data_ptr(), K_ROUND)
         else:
-            d_smp.copy_(h_smp, non_blocking=True)
-            d_heu.copy_(h_heu, non_blocking=True)
-            st = pl.expand_round_dev(d_smp.data_ptr(), d_heu.data_ptr(), K_ROUND)
+            # the reference-facing call: clrrt_expand_round with HOST buffers (pinned); the library copies them to the
+            # device inside the timed region
+            st = pl.expand_round(np_smp, np_heu)
         added = exchange() if world > 1 else st.nodes_added
         return st, added
 
@@ -223,9 +298,9 @@ def run_ours(args):
             tot_steps += st.sim_steps
             tot_roll += st.rollouts
             ms_roll += st.ms_rollout
-            # nearest_topk, ref_end, rollout<main>, select, rollout<goal-biased>, scan_block_sums, scan_sums, pack_records,
+            # nearest_topk, ref_end, order_scan, order_scatter, rollout, select, scan_block_sums, scan_sums, pack_records,
             # append_records (single GPU: appended inside the round; multi GPU: one append per rank chunk)
-            launches += 9 if world == 1 else 8 + world
+            launches += 10 if world == 1 else 9 + world
         e1.record(stream)
         if world > 1:
             dist.barrier()
@@ -239,15 +314,16 @@ def run_ours(args):
             ms, tot_steps, tot_roll = float(tmax[0]), int(t[1]), int(t[2])
         return ms, tot_steps, tot_roll, ms_roll, launches, d2h, st
 
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         one_round(True)
         pl.tree_truncate(n0)
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.mark_begin()
     ms, tot_steps, tot_roll, ms_roll, launches, _, st = timed(True, args.steps, False)
     e_ms, e_steps, e_roll, _, _, d2h, _ = timed(False, args.steps, True)
-    sampler.stop_flag = True
+    if rank == 0:
+        sampler.mark_end()
     clocks = sampler.summary() if rank == 0 else None
     if rank != 0:
         pl.close()
@@ -289,7 +365,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "fp32-pipe (CUDA cores; no tensor work on this path)", "kernel": "rollout_kernel<false>",
+        "roofline": {"bound": "fp32-pipe (CUDA cores; no tensor work on this path)", "kernel": "rollout_kernel (candidates + goal-biased continuations of one round)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s (algorithmic, SURVEY.md §8d count)",
                      "frac": achieved / peak,
                      "peak_source": f"derived: {props.multi_processor_count} SMs x 128 FP32 lanes x 2 x {sm_mhz:.0f} MHz sampled in-run",
@@ -300,8 +376,10 @@ def run_ours(args):
                              "note": "algorithmic ~190 B per rollout; HBM is idle on this path"}},
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
     pl.close()
+    if world == 1:
+        line["query_200ms"] = query_200ms_ours(clrrt, local)
+    print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -369,7 +447,7 @@ def run_reference(args):
         tree = cpu.tree_export()
     import clrrt_b200 as clrrt
     cores = os.cpu_count() or 1
-    n_per_step = 16
+    n_per_step = 64
     samples, heur = clrrt.draw_samples(GOAL, cores * (args.steps + args.warmup) * n_per_step, seed=2)
     jobs = [(w, n_per_step, args.steps, args.warmup, tree, boxes, samples, heur) for w in range(cores)]
     t0 = time.perf_counter()
@@ -390,13 +468,17 @@ def run_reference(args):
                              "sample": f"each step: {n_per_step} samples per core x {cores} independent single-threaded reference processes "
                                        f"(candidate search + top-1 rollout), {roll_total} rollouts / {steps_total} sim steps in total, wall {wall:.1f} s"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    try:
+        line["query_200ms"] = query_200ms_reference(kind)
+    except Exception as e:  # noqa: BLE001
+        line["query_200ms"] = {"error": str(e)}
     print(json.dumps(line))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -35,7 +35,7 @@ class RoundStats(C.Structure):
     _fields_ = [("samples", C.c_int32), ("rollouts", C.c_int32), ("nodes_added", C.c_int32),
                 ("goal_nodes_added", C.c_int32), ("tree_size", C.c_int32), ("reserved", C.c_int32),
                 ("sim_steps", C.c_int64), ("ms_nearest", C.c_float), ("ms_rollout", C.c_float),
-                ("ms_goal", C.c_float), ("ms_append", C.c_float)]
+                ("ms_prepare", C.c_float), ("ms_append", C.c_float)]
 
 
 class Counters(C.Structure):

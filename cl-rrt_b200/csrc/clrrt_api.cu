@@ -749,6 +749,7 @@ int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint
   job.best_rank = ctx->d_best; job.done_mask = ctx->d_done; job.res_code = ctx->d_res_code; job.res_steps = ctx->d_res_steps;
   job.out_nodes = ctx->stage; job.out_valid = ctx->d_valid;
   job.counters = ctx->d_counters; job.refill_min = ctx->refill_min; job.phase_clk = ctx->d_counters + 8;
+  CK(cudaEventRecord(ctx->ev[5], st));
   if ((rc = launch_rollout(ctx, job, n_pairs))) return rc;
   CK(cudaEventRecord(ctx->ev[2], st));
   SelectArgs sa;
@@ -783,9 +784,9 @@ int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint
     stats->nodes_added = n_new;
     stats->tree_size = ctx->n_tree;
     cudaEventElapsedTime(&stats->ms_nearest, ctx->ev[0], ctx->ev[1]);
-    cudaEventElapsedTime(&stats->ms_rollout, ctx->ev[1], ctx->ev[2]);
-    cudaEventElapsedTime(&stats->ms_goal, ctx->ev[2], ctx->ev[3]);
-    cudaEventElapsedTime(&stats->ms_append, ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&stats->ms_prepare, ctx->ev[1], ctx->ev[5]);
+    cudaEventElapsedTime(&stats->ms_rollout, ctx->ev[5], ctx->ev[2]);
+    cudaEventElapsedTime(&stats->ms_append, ctx->ev[2], ctx->ev[4]);
   }
   return CLRRT_OK;
 }

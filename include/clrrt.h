@@ -100,7 +100,9 @@ typedef struct clrrt_round_stats {
   int32_t samples, rollouts, nodes_added, goal_nodes_added, tree_size;
   int32_t reserved;
   int64_t sim_steps;
-  float ms_nearest, ms_rollout, ms_goal, ms_append; /* device time per phase (CUDA events on the ctx stream) */
+  /* device time per phase (CUDA events on the ctx stream): candidate search; the rollout kernel alone; reference ends +
+   * launch order before it; winner selection + compaction + append after it */
+  float ms_nearest, ms_rollout, ms_prepare, ms_append;
 } clrrt_round_stats;
 
 typedef struct clrrt_ctx clrrt_ctx;

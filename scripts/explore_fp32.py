@@ -26,4 +26,4 @@ boxes, smp, heu = bench.build_workload(pl2, clrrt, 0, 1)
 n0 = pl2.tree_size()
 for r in range(3):
     st = pl2.expand_round(smp, heu); pl2.tree_truncate(n0)
-print(f"fp32 C3 round: rollouts {st.rollouts} steps {st.sim_steps} nodes+{st.nodes_added} ms nearest {st.ms_nearest:.2f} rollout {st.ms_rollout:.2f} goal {st.ms_goal:.2f} -> {st.sim_steps/(st.ms_nearest+st.ms_rollout+st.ms_goal+st.ms_append)*1e3:.3e} steps/s")
+print(f"fp32 C3 round: rollouts {st.rollouts} steps {st.sim_steps} nodes+{st.nodes_added} ms nearest {st.ms_nearest:.2f} rollout {st.ms_rollout:.2f} goal {st.ms_prepare:.2f} -> {st.sim_steps/(st.ms_nearest+st.ms_rollout+st.ms_prepare+st.ms_append)*1e3:.3e} steps/s")

@@ -78,7 +78,7 @@ for r in range(3):
     orc.expand_round(s, h); st = pl.expand_round(s, h)
     a, b = pl.tree_download_records(), orc.tree_export()
     same_disc = len(a) == len(b) and np.array_equal(a[:, [7, 17, 18, 19]], b[:, [7, 17, 18, 19]])
-    print(f"round {r}: gpu {len(a)} oracle {len(b)} discrete equal {same_disc} allclose {len(a)==len(b) and np.allclose(a, b, rtol=1e-6, atol=1e-9)} stats nodes+{st.nodes_added} steps {st.sim_steps} ms {st.ms_nearest:.3f}/{st.ms_rollout:.3f}/{st.ms_goal:.3f}/{st.ms_append:.3f}")
+    print(f"round {r}: gpu {len(a)} oracle {len(b)} discrete equal {same_disc} allclose {len(a)==len(b) and np.allclose(a, b, rtol=1e-6, atol=1e-9)} stats nodes+{st.nodes_added} steps {st.sim_steps} ms {st.ms_nearest:.3f}/{st.ms_rollout:.3f}/{st.ms_prepare:.3f}/{st.ms_append:.3f}")
 # C3-size timing
 boxes = scene_c3_boxes()
 orc = CpuPlanner("oracle"); orc.set_obstacles(boxes); orc.srand(1); orc.tree_init((0, 0, 0, 0, 3, 0), (100, 0, 0, 0), 5.0); orc.expand(300)
@@ -88,8 +88,8 @@ n0 = pl2.tree_size()
 s, h, _ = orc.draw_samples(65536)
 for r in range(3):
     st = pl2.expand_round(s, h); pl2.tree_truncate(n0)
-    print(f"C3 round: K=65536 tree {n0} nodes+{st.nodes_added} rollouts {st.rollouts} steps {st.sim_steps} ms nearest {st.ms_nearest:.3f} rollout {st.ms_rollout:.3f} goal {st.ms_goal:.3f} append {st.ms_append:.3f} -> {st.sim_steps/ (st.ms_rollout+st.ms_goal) * 1e3:.3e} steps/s")
+    print(f"C3 round: K=65536 tree {n0} nodes+{st.nodes_added} rollouts {st.rollouts} steps {st.sim_steps} ms nearest {st.ms_nearest:.3f} rollout {st.ms_rollout:.3f} goal {st.ms_prepare:.3f} append {st.ms_append:.3f} -> {st.sim_steps/ (st.ms_rollout+st.ms_prepare) * 1e3:.3e} steps/s")
 pl2.set_obstacles(scene_c1_boxes())
 for r in range(2):
     st = pl2.expand_round(s, h); pl2.tree_truncate(n0)
-    print(f"C2-like round (10 boxes): rollouts {st.rollouts} steps {st.sim_steps} ms nearest {st.ms_nearest:.3f} rollout {st.ms_rollout:.3f} goal {st.ms_goal:.3f} -> {st.sim_steps/ (st.ms_rollout+st.ms_goal) * 1e3:.3e} steps/s")
+    print(f"C2-like round (10 boxes): rollouts {st.rollouts} steps {st.sim_steps} ms nearest {st.ms_nearest:.3f} rollout {st.ms_rollout:.3f} goal {st.ms_prepare:.3f} -> {st.sim_steps/ (st.ms_rollout+st.ms_prepare) * 1e3:.3e} steps/s")

@@ -12,6 +12,6 @@ for K in (bench.K_ROUND, 4096):
     best = None
     for r in range(4):
         st = pl.expand_round(smp[:K], heu[:K]); pl.tree_truncate(n0)
-        t = (st.ms_nearest, st.ms_rollout, st.ms_goal, st.ms_append)
+        t = (st.ms_nearest, st.ms_rollout, st.ms_prepare, st.ms_append)
         if best is None or sum(t) < sum(best): best = t
     print(f"{tag}: K={K} rollouts {st.rollouts} steps {st.sim_steps} added {st.nodes_added} ms nearest {best[0]:.2f} rollout {best[1]:.2f} goal {best[2]:.2f} append {best[3]:.2f} total {sum(best):.2f}")

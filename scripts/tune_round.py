@@ -13,7 +13,7 @@ n0 = pl.tree_size()
 def run(tag, K=bench.K_ROUND, reps=2):
     for r in range(reps):
         st = pl.expand_round(smp[:K], heu[:K]); pl.tree_truncate(n0)
-    print(f"{tag}: K={K} rollouts {st.rollouts} steps {st.sim_steps} ms nearest {st.ms_nearest:.2f} rollout {st.ms_rollout:.2f} goal {st.ms_goal:.2f} append {st.ms_append:.2f} -> {st.sim_steps/(st.ms_rollout+st.ms_goal)*1e3:.3e} steps/s (kernels), {st.sim_steps/(st.ms_rollout)*1e3:.3e} main only")
+    print(f"{tag}: K={K} rollouts {st.rollouts} steps {st.sim_steps} ms nearest {st.ms_nearest:.2f} rollout {st.ms_rollout:.2f} goal {st.ms_prepare:.2f} append {st.ms_append:.2f} -> {st.sim_steps/(st.ms_rollout+st.ms_prepare)*1e3:.3e} steps/s (kernels), {st.sim_steps/(st.ms_rollout)*1e3:.3e} main only")
 for bps in (0,):
     for rf in (1, 8, 16, 32):
         pl.set_tuning(refill_min=rf, blocks_per_sm=bps)
