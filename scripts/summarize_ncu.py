@@ -31,10 +31,13 @@ want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum"]
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
+        "smsp__inst_executed_pipe_fp64.sum", "smsp__inst_executed_pipe_fma.sum", "smsp__inst_executed_pipe_alu.sum", "smsp__inst_executed_pipe_xu.sum",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct"]
 with open(os.path.join(out, f"{tag}_rollout_kernel_ncu.md"), "w") as f:
-    f.write(f"# ncu --set full ({tag}): rollout kernels of one C3 round (65536 samples, 1000 obstacles, 4096-node tree)\n\n"
-            "`ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 8 -c 2 python bench.py --steps 2 --warmup 1 --no-cpu-baseline`\n\n")
+    f.write(f"# ncu --set full ({tag}): candidate search and rollout kernel of one C3 round (65536 samples, 1000 obstacles, 4096-node tree)\n\n"
+            "`ncu --set full --clock-control none --import-source on -k 'regex:rollout_kernel|nearest_topk_kernel' -s 6 -c 2 python bench.py --steps 2 --warmup 1 --no-cpu-baseline`\n\n")
     cols = [i for i in range(2, len(r))]
     f.write("| metric | unit | " + " | ".join(f"launch {i-2}" for i in cols) + " |\n|---|---|" + "---|" * len(cols) + "\n")
     for w in want:
