@@ -174,12 +174,20 @@ int ensure_params(clrrt_ctx* ctx) {
 
 template <typename R> int configure_launch_t(clrrt_ctx* ctx) {
   const int sm = (int)ctx->smem_bytes;
-  CK(cudaFuncSetAttribute(rollout_kernel<R, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  CK(cudaFuncSetAttribute(rollout_kernel<R, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  int b0 = 1;
-  if (ctx->dprm.exact_dist) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rollout_kernel<R, 2, true>, ROLLOUT_THREADS, ctx->smem_bytes));
-  else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rollout_kernel<R, 2, false>, ROLLOUT_THREADS, ctx->smem_bytes));
+  CK(cudaFuncSetAttribute(rollout_kernel<R, 2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(rollout_kernel<R, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(rollout_kernel<R, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(rollout_kernel<R, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  int b0 = 1, b1 = 1;
+  if (ctx->dprm.exact_dist) {
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rollout_kernel<R, 2, true, true>, ROLLOUT_THREADS, ctx->smem_bytes));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, rollout_kernel<R, 2, true, false>, ROLLOUT_THREADS, ctx->smem_bytes));
+  } else {
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rollout_kernel<R, 2, false, true>, ROLLOUT_THREADS, ctx->smem_bytes));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, rollout_kernel<R, 2, false, false>, ROLLOUT_THREADS, ctx->smem_bytes));
+  }
   ctx->blocks_per_sm_main = std::max(1, b0);
+  ctx->blocks_per_sm_gb = std::max(1, b1);
   return CLRRT_OK;
 }
 
@@ -188,24 +196,26 @@ int configure_launch(clrrt_ctx* ctx) {
   return ctx->prm.fp32 ? configure_launch_t<float>(ctx) : configure_launch_t<double>(ctx);
 }
 
-// One kernel for everything: plain and goal-biased rollouts are told apart per lane at run time (GBM = 2).
-template <typename R> int launch_rollout_t(clrrt_ctx* ctx, const RolloutJob& job, int blocks) {
+// One kernel per mode (round / batch): plain and goal-biased rollouts are told apart per lane at run time (GBM = 2).
+template <typename R, bool ROUND> int launch_rollout_t(clrrt_ctx* ctx, const RolloutJob& job, int blocks) {
   if (ctx->dprm.exact_dist)
-    rollout_kernel<R, 2, true><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells);
+    rollout_kernel<R, 2, true, ROUND><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells);
   else
-    rollout_kernel<R, 2, false><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells);
+    rollout_kernel<R, 2, false, ROUND><<<blocks, ROLLOUT_THREADS, ctx->smem_bytes, ctx->stream>>>(job, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells);
   CK(cudaGetLastError());
   return CLRRT_OK;
 }
 
 int launch_rollout(clrrt_ctx* ctx, const RolloutJob& job, int n_items_hint) {
-  int per_sm = ctx->blocks_per_sm_main;
+  const bool round = job.best_rank != nullptr;
+  int per_sm = round ? ctx->blocks_per_sm_main : ctx->blocks_per_sm_gb;
   if (ctx->blocks_override > 0) per_sm = std::min(per_sm, ctx->blocks_override);
   const int lanes_per_block = ROLLOUT_THREADS;
   int blocks = ctx->num_sms * per_sm;  // persistent grid: a multiple of the SM count
   const int needed = (n_items_hint + lanes_per_block - 1) / lanes_per_block;
   if (needed < blocks) blocks = std::max(1, needed);
-  return ctx->prm.fp32 ? launch_rollout_t<float>(ctx, job, blocks) : launch_rollout_t<double>(ctx, job, blocks);
+  if (round) return ctx->prm.fp32 ? launch_rollout_t<float, true>(ctx, job, blocks) : launch_rollout_t<double, true>(ctx, job, blocks);
+  return ctx->prm.fp32 ? launch_rollout_t<float, false>(ctx, job, blocks) : launch_rollout_t<double, false>(ctx, job, blocks);
 }
 
 }  // namespace
