@@ -88,6 +88,34 @@ void MyRRT::addInitialNode(const std::vector<double>& state) {
   n.parent = -1; n.n_ref = N;
   ck(ctx_, clrrt_tree_reset(ctx_, &n, 1), "clrrt_tree_reset");
 }
+void MyRRT::reconfigure(const std::vector<double>& goal, double vmax, double car_speed, const PlannerParams& prm) {
+  if (goal.size() < 4) throw Error("goalPose needs 4 entries");
+  goalPose = goal;
+  prm_.ref_res = std::max(std::abs(car_speed) * prm.ref_int, prm.ref_mindist);  // controller.cpp:18-21
+  prm_.vmax = vmax;
+  for (int i = 0; i < 5; i++) { prm_.Wcost[i] = prm.Wcost[i]; Wcost[i] = prm.Wcost[i]; }
+  for (int i = 0; i < 4; i++) prm_.goal[i] = goalPose[i];
+  prm_.obs_use_pred = prm.obs_use_pred ? 1 : 0;
+  carried_.clear();
+  ck(ctx_, clrrt_set_params(ctx_, &prm_), "clrrt_set_params");
+}
+void MyRRT::setCarriedTree(const std::vector<Node>& nodes) {
+  std::vector<clrrt_node> c(nodes.size());
+  for (size_t i = 0; i < nodes.size(); i++) {
+    const Node& nd = nodes[i];
+    clrrt_node& n = c[i];
+    memset(&n, 0, sizeof n);
+    for (int k = 0; k < 10 && k < (int)nd.state.size(); k++) n.state[k] = nd.state[k];
+    if (nd.ref.x.empty() || nd.ref.v.empty()) throw Error("carried node without a reference");
+    n.ref_front[0] = nd.ref.x.front(); n.ref_front[1] = nd.ref.y.front();
+    n.ref_back[0] = nd.ref.x.back(); n.ref_back[1] = nd.ref.y.back();
+    n.ref_vback = nd.ref.v.back();
+    n.costE = nd.costE; n.costS = nd.costS; n.parent = nd.parentID; n.goal_reached = nd.goalReached ? 1 : 0;
+    n.n_ref = (int)nd.ref.x.size(); n.kind = 0;
+  }
+  ck(ctx_, clrrt_tree_reset(ctx_, c.data(), (int)c.size()), "clrrt_tree_reset");
+  carried_ = nodes;
+}
 void MyRRT::setObstacles(const std::vector<Obstacle2D>& d) {
   det = d;
   std::vector<clrrt_obstacle> o(d.size());
@@ -108,11 +136,53 @@ std::vector<Node> MyRRT::tree() const {
   return out;
 }
 
-void initializeTree(MyRRT& RRT, const Vehicle&, std::vector<Node>& nodes, std::vector<double>& carState) {
+double getNodeCost(const MyRRT& RRT, const Vehicle& veh, const double& parentCost, const Node& node, double sim_dt) {
+  // rrt/src/rrtplanner.cpp:105-119.  checkObsDistance(RRT.carState) is the shipped stub there (collisioncheck.cpp:6-8),
+  // also in a build with obstacles: carState has 6 entries at that point, which the obstacle overload rejects
+  double cost = parentCost;
+  for (auto it = node.tra.begin(); it != node.tra.end(); it++) {
+    double Dobs = 100;
+    double kappa = tan((*it)[3]) / veh.L;
+    cost += RRT.Wcost[0] * (*it)[4] * sim_dt + RRT.Wcost[1] * std::abs(kappa) + RRT.Wcost[2] * exp(-RRT.Wcost[3] * Dobs);
+  }
+  return cost;
+}
+
+void initializeTree(MyRRT& RRT, const Vehicle& veh, std::vector<Node>& nodes, std::vector<double>& carState) {
   // rrt/src/rrtplanner.cpp:39-48: four logging slots appended, empty committed path -> root node
   carState.push_back(0); carState.push_back(0); carState.push_back(0); carState.push_back(0);
-  if (!nodes.empty()) throw Error("carried-over trees (commit_path=true) are outside this round's scope");
-  RRT.addInitialNode(carState);
+  if (nodes.size() == 0) {
+    RRT.addInitialNode(carState);
+    return;
+  }
+  // :51-57 erase nodes that end behind the vehicle (upstream erases through `nodes.erase(it--)`: same survivors)
+  for (auto it = nodes.begin(); it != nodes.end();) {
+    it->goalReached = 0;
+    if (it->tra.empty()) throw Error("carried node without a trajectory");
+    if ((it->tra.back()[0]) < 0) it = nodes.erase(it);
+    else ++it;
+  }
+  if (nodes.empty()) {  // upstream reads nodes.front() of an empty vector here (undefined); defined as the empty tree
+    RRT.addInitialNode(carState);
+    return;
+  }
+  // :59-70 goal flags from the trajectories (the y distance ignores the goal's y, as upstream)
+  for (auto it = nodes.begin(); it != nodes.end(); ++it) {
+    for (size_t i = 0; i != it->tra.size(); i++) {
+      double Dgoal = sqrt(pow(it->tra[i][0] - RRT.goalPose[0], 2) + pow(it->tra[i][1], 2));
+      double Hgoal = std::abs(it->tra[i][2] - RRT.goalPose[2]);
+      double dVgoal = std::abs(it->tra[i][4] - RRT.goalPose[3]);
+      if ((Dgoal <= 1) && (Hgoal <= 0.05) && (dVgoal <= 0.1)) it->goalReached = 1;
+    }
+  }
+  // :72-82 the collision re-check calls the shipped stub (Dobs = 100): it never fires
+  // :84-88 cost estimates along the chain (Node::costS is float)
+  const double dt = RRT.params().sim_dt;
+  nodes.front().costS = getNodeCost(RRT, veh, 0, nodes.front(), dt);
+  for (size_t i = 1; i != nodes.size(); i++) nodes[i].costS = getNodeCost(RRT, veh, nodes[i - 1].costS, nodes[i], dt);
+  // :90-93 re-parent as a chain and make it the tree
+  for (size_t i = 0; i != nodes.size(); i++) nodes[i].parentID = (int)i - 1;
+  RRT.setCarriedTree(nodes);
 }
 
 clrrt_round_stats expandTree(Vehicle&, MyRRT& RRT, int K) {
@@ -164,9 +234,19 @@ std::vector<Node> extractBestPath(MyRRT& RRT, std::vector<int32_t>* ids_out) {
   for (int i = 0; i < len; i++) best.push_back(node_from_c(c[i]));
   // Node::tra / Node::ref: the device tree keeps end points only.  Every node records the sample its reference was
   // aimed at and whether it was a goal-biased expansion, which with its parent re-creates the rollout exactly.
-  best[0].tra = {best[0].state};  // root: addInitialNode stores the single start state (rrtplanner.cpp:34)
-  for (int i = 1; i < len; i++) {
-    if (c[i].kind == 0) { best[i].tra = {best[i].state}; continue; }
+  const std::vector<Node>& carried = RRT.carried();
+  for (int i = 0; i < len; i++) {
+    if (ids[i] < (int)carried.size()) { best[i] = carried[ids[i]]; continue; }  // carried node: the host copy is complete
+    if (c[i].kind == 0) {
+      // root: addInitialNode stores the single start state and the 10-point reference (0,0)->(1,0), rrtplanner.cpp:21-37
+      best[i].tra = {best[i].state};
+      const int N = std::max(c[i].n_ref, 2);
+      best[i].ref.x = LinearSpacedVector(0, 1, N);
+      best[i].ref.y = LinearSpacedVector(0, 0, N);
+      best[i].ref.v.assign((size_t)N, best[i].state[4]);
+      best[i].ref.dir = 1;
+      continue;
+    }
     clrrt_rollout r;
     rematerialise(RRT, ids[i - 1], c[i].sample, c[i].kind == 2, r, best[i].tra, best[i].ref);
   }
@@ -207,6 +287,19 @@ void filterMPCmessage(Trajectory& msg) {
   }
   msg = f;
 }
+void transformNodesWorldToCar(std::vector<Node>& nodes, const std::vector<double> carPose) {
+  auto pt = [&](double& Xw, double& Yw) {  // transformPointWorldToCar, rrt/src/transformations.cpp:6-10
+    double Xc = Xw * cos(carPose[2]) - carPose[0] * cos(carPose[2]) - carPose[1] * sin(carPose[2]) + Yw * sin(carPose[2]);
+    double Yc = Yw * cos(carPose[2]) - carPose[1] * cos(carPose[2]) + carPose[0] * sin(carPose[2]) - Xw * sin(carPose[2]);
+    Xw = Xc; Yw = Yc;
+  };
+  for (auto& n : nodes) {
+    pt(n.state[0], n.state[1]);
+    n.state[2] -= carPose[2];
+    for (size_t i = 0; i < n.ref.x.size(); i++) pt(n.ref.x[i], n.ref.y[i]);
+    for (auto& s : n.tra) pt(s[0], s[1]);  // trajectory headings are left as they are, as upstream (:310-313)
+  }
+}
 void transformNodesCarToworld(std::vector<Node>& nodes, const std::vector<double> carPose) {
   auto pt = [&](double& Xc, double& Yc) {  // transformPointCarToWorld, rrt/src/transformations.cpp:13-17
     double Xw = cos(carPose[2]) * Xc - sin(carPose[2]) * Yc + carPose[0];
@@ -234,18 +327,31 @@ bool MotionPlanner::resetPlanner() {
   motionplan.clear();
   return true;
 }
+MotionPlanner::~MotionPlanner() { delete rrt_; }
 void MotionPlanner::planMotion(MotionRequest req) {
   Vehicle veh; veh.setPrius();                                  // :13
   std::vector<double> worldState = state;                       // :14
   std::vector<double> carPose = worldState;                     // transformStateToLocal, transformations.cpp:143-147
   carPose[0] = 0; carPose[1] = 0; carPose[2] = 0;
   updateObstacles();                                            // :18
-  MyRRT RRT(req.goal, req.laneShifts, req.Cxy, req.bend, veh, params, req.vmax, carPose[4], device, 1 << 18,
-            std::max(samplesPerRound, 1));                      // :16-17, :23
+  transformNodesWorldToCar(bestNodes, worldState);              // :22
+  // :16-17, :23 — the device context is kept across queries; a query only changes its parameters
+  const int round = std::max(samplesPerRound, 1);
+  if (rrt_ && rrt_round_ != round) { delete rrt_; rrt_ = nullptr; }
+  if (!rrt_) {
+    rrt_ = new MyRRT(req.goal, req.laneShifts, req.Cxy, req.bend, veh, params, req.vmax, carPose[4], device, treeCapacity, round);
+    rrt_round_ = round;
+  } else {
+    if (req.bend) throw Error("bend=true (curved-road mode) is outside the accelerated path");
+    rrt_->reconfigure(req.goal, req.vmax, carPose[4], params);
+  }
+  MyRRT& RRT = *rrt_;
   RRT.setObstacles(det);                                        // :24
   RRT.carState = carPose;
   if (!params.commit_path) bestNodes.clear();                   // :28-30
   initializeTree(RRT, veh, bestNodes, carPose);                 // :32
+  lastCarried = (int)RRT.carried().size();
+  lastInitialTree = RRT.treeSize();
   int iter = 0;                                                 // :39-43
   auto t0 = std::chrono::steady_clock::now();
   for (;; iter++) {
@@ -258,9 +364,11 @@ void MotionPlanner::planMotion(MotionRequest req) {
   clrrt_counters_get(RRT.ctx(), &lastCounters);                 // :45
   bestNodes = extractBestPath(RRT, &lastBestIds);               // :51
   lastRematError = 0;
-  for (const Node& n : bestNodes)
-    if (!n.tra.empty())
-      for (int k = 0; k < 10; k++) lastRematError = std::max(lastRematError, std::abs(n.tra.back()[k] - n.state[k]));
+  for (size_t i = 0; i < bestNodes.size(); i++) {
+    const Node& n = bestNodes[i];
+    if (lastBestIds[i] < lastCarried || n.tra.empty()) continue;  // carried nodes were not re-created
+    for (int k = 0; k < 10; k++) lastRematError = std::max(lastRematError, std::abs(n.tra.back()[k] - n.state[k]));
+  }
   transformNodesCarToworld(bestNodes, worldState);              // :54
   lastTrajectory = Trajectory();
   if (bestNodes.size() == 0) return;                            // :56-58
@@ -315,4 +423,76 @@ extern "C" int clrrt_host_plan_motion(const double* car_state6, const double* go
     fprintf(stderr, "clrrt_host_plan_motion: %s\n", e.what());
     return CLRRT_ERR_STATE;
   }
+}
+
+// ---- persistent planner handle: consecutive queries (receding-horizon loop, config C5) ----------------------------
+extern "C" void* clrrt_host_planner_create(int device, int samples_per_round, int commit_path, int tree_capacity) {
+  clrrt::MotionPlanner* mp = new clrrt::MotionPlanner();
+  mp->device = device;
+  mp->samplesPerRound = samples_per_round;
+  mp->params.commit_path = commit_path != 0;
+  if (tree_capacity > 0) mp->treeCapacity = tree_capacity;
+  return mp;
+}
+extern "C" void clrrt_host_planner_destroy(void* h) { delete static_cast<clrrt::MotionPlanner*>(h); }
+// One planMotion call.  goal4 and obs are in the car frame, as the planner receives them.  sizes4 = {nodes of
+// the initial tree (1 = root only), final tree size, nodes of the best path, expandTree calls}.
+extern "C" int clrrt_host_planner_query(void* h, const double* world_state6, const double* goal4, double vmax,
+                                        const clrrt_obstacle* obs, int n_obs, int max_iterations, double budget_ms,
+                                        int32_t* sizes4, double* best_cost, clrrt_counters* counters) {
+  try {
+    clrrt::MotionPlanner& mp = *static_cast<clrrt::MotionPlanner*>(h);
+    mp.maxIterations = max_iterations;
+    mp.budget_ms = budget_ms;
+    std::vector<clrrt::Obstacle2D> det((size_t)n_obs);
+    for (int i = 0; i < n_obs; i++) {
+      det[i].obb.center.x = obs[i].cx; det[i].obb.center.y = obs[i].cy; det[i].obb.center.theta = obs[i].theta;
+      det[i].obb.size_x = obs[i].size_x; det[i].obb.size_y = obs[i].size_y;
+      det[i].vel.linear.x = obs[i].vx; det[i].vel.linear.y = obs[i].vy;
+    }
+    mp.getobstacles = [det]() { return det; };
+    mp.updateState(std::vector<double>(world_state6, world_state6 + 6));
+    clrrt::MotionRequest req;
+    req.goal.assign(goal4, goal4 + 4);
+    req.vmax = vmax;
+    req.laneShifts = {0};
+    mp.planMotion(req);
+    if (sizes4) {
+      sizes4[0] = mp.lastInitialTree; sizes4[1] = mp.lastTreeSize; sizes4[2] = (int)mp.bestNodes.size(); sizes4[3] = mp.lastIterations;
+    }
+    if (best_cost) *best_cost = mp.bestNodes.empty() ? -1.0 : (double)mp.bestNodes.back().costS;
+    if (counters) *counters = mp.lastCounters;
+    return CLRRT_OK;
+  } catch (const std::exception& e) {
+    fprintf(stderr, "clrrt_host_planner_query: %s\n", e.what());
+    return CLRRT_ERR_STATE;
+  }
+}
+// bestNodes of the last query (world frame): {state[10], ref front xy, ref back xy, ref.v.back(), costE, costS,
+// parentID, goalReached, ref.x.size()} per node; returns the node count
+extern "C" int clrrt_host_planner_best_nodes(void* h, double* rec20, int cap) {
+  const clrrt::MotionPlanner& mp = *static_cast<clrrt::MotionPlanner*>(h);
+  int n = 0;
+  for (const clrrt::Node& nd : mp.bestNodes) {
+    if (n >= cap) break;
+    double* o = rec20 + (size_t)20 * n++;
+    for (int k = 0; k < 10; k++) o[k] = nd.state[k];
+    o[10] = nd.ref.x.front(); o[11] = nd.ref.y.front(); o[12] = nd.ref.x.back(); o[13] = nd.ref.y.back();
+    o[14] = nd.ref.v.empty() ? 0.0 : nd.ref.v.back();
+    o[15] = nd.costE; o[16] = nd.costS; o[17] = nd.parentID; o[18] = nd.goalReached ? 1 : 0; o[19] = (double)nd.ref.x.size();
+  }
+  return (int)mp.bestNodes.size();
+}
+extern "C" int clrrt_host_planner_best_traj(void* h, double* traj10, int cap_rows, int32_t* rows_per_node, int cap_nodes) {
+  const clrrt::MotionPlanner& mp = *static_cast<clrrt::MotionPlanner*>(h);
+  int rows = 0, n = 0;
+  for (const clrrt::Node& nd : mp.bestNodes) {
+    if (n < cap_nodes) rows_per_node[n] = (int)nd.tra.size();
+    n++;
+    for (const auto& x : nd.tra) {
+      if (rows < cap_rows) for (int k = 0; k < 10; k++) traj10[(size_t)10 * rows + k] = x[k];
+      rows++;
+    }
+  }
+  return rows;
 }

@@ -102,6 +102,12 @@ class MyRRT {
   MyRRT& operator=(const MyRRT&) = delete;
 
   void addInitialNode(const std::vector<double>& state);  // rrt/src/rrtplanner.cpp:21-37
+  // the carried-over chain of initializeTree's non-empty branch (rrt/src/rrtplanner.cpp:89-93): uploaded as the initial
+  // tree; the host copies keep the full references and trajectories for extractBestPath
+  void setCarriedTree(const std::vector<Node>& nodes);
+  const std::vector<Node>& carried() const { return carried_; }
+  // next query on the same device context: goal, vmax and the reference resolution change (motionplanner.cpp:16-23)
+  void reconfigure(const std::vector<double>& goalPose, double vmax, double car_speed, const PlannerParams& prm);
   void setObstacles(const std::vector<Obstacle2D>& det);  // RRT.det = det, rrt/src/motionplanner.cpp:24
   int treeSize() const;
   std::vector<Node> tree() const;                          // download (ref = front/back points)
@@ -111,6 +117,7 @@ class MyRRT {
  private:
   clrrt_ctx* ctx_ = nullptr;
   clrrt_params prm_;
+  std::vector<Node> carried_;
 };
 
 // expandTree (rrt/src/rrtplanner.cpp:123-174), K samples per call against one tree snapshot.  K == 1 is the
@@ -118,8 +125,12 @@ class MyRRT {
 clrrt_round_stats expandTree(Vehicle& veh, MyRRT& RRT, int K = 1);
 // extractBestPath (rrt/src/rrtplanner.cpp:318-368) with the trajectories of the returned nodes re-materialised.
 std::vector<Node> extractBestPath(MyRRT& RRT, std::vector<int32_t>* ids_out = nullptr);
-// initializeTree (rrt/src/rrtplanner.cpp:39-48): empty committed path -> single root node
+// initializeTree (rrt/src/rrtplanner.cpp:39-95): empty committed path -> single root node; otherwise the previous best
+// path (already in the car frame) becomes the initial tree: nodes ending behind the car are dropped, goal flags and the
+// costS chain are recomputed from the stored trajectories, the nodes are re-parented as a chain.
 void initializeTree(MyRRT& RRT, const Vehicle& veh, std::vector<Node>& nodes, std::vector<double>& carState);
+// getNodeCost (rrt/src/rrtplanner.cpp:105-119)
+double getNodeCost(const MyRRT& RRT, const Vehicle& veh, const double& parentCost, const Node& node, double sim_dt);
 
 // rrt/include/rrt/simulation.h:7-26.  As upstream, everything happens in the constructor.  The rollout starts at
 // tree node `parent` (the reference passes that node's state and a reference built from it, rrtplanner.cpp:151-152)
@@ -155,17 +166,26 @@ struct MotionPlanner {
   std::vector<int32_t> lastBestIds;   // tree indices of bestNodes
   double lastRematError = 0;          // max |tra.back() - node.state| over the best path (0: re-materialisation is exact)
   clrrt_counters lastCounters{};
+  int lastCarried = 0;                // nodes of the previous best path the tree was initialised with (commit_path)
+  int lastInitialTree = 0;            // tree size after initializeTree (1 = root only)
+  int treeCapacity = 1 << 18;
+  ~MotionPlanner();
 
   void planMotion(MotionRequest req);                       // rrt/src/motionplanner.cpp:8-77
   bool updateObstacles();                                   // rrt/src/motionplanner.cpp:81-86
   void updateState(const std::vector<double>& msg_state);   // rrt/src/motionplanner.cpp:89-94
   bool resetPlanner();                                      // rrt/src/motionplanner.cpp:98-100
+
+ private:
+  MyRRT* rrt_ = nullptr;              // one device context for all queries of this planner
+  int rrt_round_ = 0;
 };
 
 std::vector<Path> convertNodesToPath(const std::vector<Node>& path);   // rrt/src/motionplanner.cpp:264-275
 Trajectory generateMPCmessage(const std::vector<Path>& path);          // rrt/src/motionplanner.cpp:103-128
 void filterMPCmessage(Trajectory& msg);                                // rrt/src/motionplanner.cpp:130-150
 void transformNodesCarToworld(std::vector<Node>& nodes, const std::vector<double> carState);  // transformations.cpp:289-301
+void transformNodesWorldToCar(std::vector<Node>& nodes, const std::vector<double> carState);  // transformations.cpp:303-315
 
 }  // namespace clrrt
 
@@ -175,4 +195,12 @@ int clrrt_host_plan_motion(const double* car_state6, const double* goal4, double
                            int n_obs, int samples_per_round, int max_iterations, double budget_ms, unsigned seed,
                            int device, int* tree_size, int* iterations, clrrt_counters* counters, double* traj8,
                            int traj_cap, int* traj_len, int32_t* best_ids, int best_cap, int* best_len, double* remat_err);
+// persistent planner: consecutive queries with MotionPlanner::bestNodes carried over (commit_path)
+void* clrrt_host_planner_create(int device, int samples_per_round, int commit_path, int tree_capacity);
+void clrrt_host_planner_destroy(void* h);
+int clrrt_host_planner_query(void* h, const double* world_state6, const double* goal4, double vmax, const clrrt_obstacle* obs,
+                             int n_obs, int max_iterations, double budget_ms, int32_t* sizes4, double* best_cost,
+                             clrrt_counters* counters);
+int clrrt_host_planner_best_nodes(void* h, double* rec20, int cap);
+int clrrt_host_planner_best_traj(void* h, double* traj10, int cap_rows, int32_t* rows_per_node, int cap_nodes);
 }

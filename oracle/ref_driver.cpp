@@ -408,4 +408,68 @@ int ref_best_path(int* ids, int cap) {
   for (int i = 0; i < n; i++) ids[i] = chain[i];
   return (int)best.size();
 }
+// ---- receding-horizon queries with a carried-over tree (config C5) ------------------------------
+// MotionPlanner::planMotion (rrt/src/motionplanner.cpp:8-54) with commit_path = true, restated as the same sequence
+// of calls into the reference's own functions — transformNodesWorldToCar, MyRRT, initializeTree (non-empty branch,
+// rrt/src/rrtplanner.cpp:50-94), expandTree, extractBestPath, transformNodesCarToworld — with `iters` expandTree calls
+// in place of Timer(200) so that the result is deterministic.  Goal and obstacles are given in the car frame, as the
+// planner receives them from the mission planner / detection node.  MotionPlanner::bestNodes lives in g_bestNodes.
+static vector<Node> g_bestNodes;
+void ref_commit_reset(void) { g_bestNodes.clear(); }
+int ref_query_commit(const double* world_state6, const double* goal4, double vmax_, int iters, int* sizes4, double* best_cost) {
+  commit_path = true;
+  fail_acclimit = 0; fail_collision = 0; fail_iterlimit = 0; sim_count = 0;
+  vector<double> worldState(world_state6, world_state6 + 6);
+  vector<double> carPose = transformStateToLocal(worldState);
+  updateLookahead(carPose[4]);
+  updateReferenceResolution(carPose[4]);
+  vmax = vmax_;
+  vgoal = goal4[3];
+  transformNodesWorldToCar(g_bestNodes, worldState);
+  g_goal.assign(goal4, goal4 + 4);
+  delete g_rrt;
+  vector<double> laneShifts{0}, Cxy;
+  g_rrt = new MyRRT(g_goal, laneShifts, Cxy, false);
+  g_rrt->det = g_obstacles;
+  g_rrt->carState = carPose;
+  g_carState = carPose;
+  initializeTree(*g_rrt, g_veh, g_bestNodes, carPose);
+  sizes4[0] = (int)g_rrt->tree.size();
+  for (int i = 0; i < iters; i++) expandTree(g_veh, *g_rrt, nullptr, g_obstacles, Cxy);
+  sizes4[1] = (int)g_rrt->tree.size();
+  g_bestNodes = extractBestPath(g_rrt->tree, nullptr);
+  sizes4[2] = (int)g_bestNodes.size();
+  sizes4[3] = sim_count;
+  if (best_cost) *best_cost = g_bestNodes.empty() ? -1.0 : (double)g_bestNodes.back().costS;
+  transformNodesCarToworld(g_bestNodes, worldState);
+  commit_path = false;
+  return sizes4[1];
+}
+// bestNodes after the last query (world frame): per node {state[10], ref front xy, ref back xy, ref.v.back(), costE,
+// costS, parentID, goalReached, ref.x.size()}; returns the node count
+int ref_best_nodes(double* rec20, int cap) {
+  int n = 0;
+  for (const Node& nd : g_bestNodes) {
+    if (n >= cap) break;
+    double* o = rec20 + (size_t)NODE_STRIDE * n++;
+    for (int k = 0; k < 10; k++) o[k] = nd.state[k];
+    o[10] = nd.ref.x.front(); o[11] = nd.ref.y.front(); o[12] = nd.ref.x.back(); o[13] = nd.ref.y.back();
+    o[14] = nd.ref.v.empty() ? 0.0 : nd.ref.v.back();
+    o[15] = nd.costE; o[16] = nd.costS; o[17] = nd.parentID; o[18] = nd.goalReached; o[19] = (double)nd.ref.x.size();
+  }
+  return (int)g_bestNodes.size();
+}
+// concatenated trajectories of bestNodes (rows of 10 doubles, world x/y, headings as stored); rows_per_node[i] = tra.size()
+int ref_best_traj(double* traj10, int cap_rows, int* rows_per_node, int cap_nodes) {
+  int rows = 0, n = 0;
+  for (const Node& nd : g_bestNodes) {
+    if (n < cap_nodes) rows_per_node[n] = (int)nd.tra.size();
+    n++;
+    for (const auto& x : nd.tra) {
+      if (rows < cap_rows) for (int k = 0; k < 10; k++) traj10[(size_t)10 * rows + k] = x[k];
+      rows++;
+    }
+  }
+  return rows;
+}
 }  // extern "C"

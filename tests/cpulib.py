@@ -104,6 +104,31 @@ class CpuPlanner:
         n = self._f("expand_timed")(C.c_double(budget_ms), C.byref(it))
         return n, it.value
 
+    # ---- receding-horizon queries with a carried tree (reference libraries only, config C5) --------------
+    def commit_reset(self):
+        self._f("commit_reset")()
+
+    def query_commit(self, world_state6, goal4_car, vmax, iters):
+        """One planMotion query with commit_path = true (see oracle/ref_driver.cpp: ref_query_commit).
+        Returns (carried nodes in the initial tree, final tree size, best path nodes, sim steps, best cost)."""
+        w = np.ascontiguousarray(world_state6, dtype=np.float64)
+        g = np.ascontiguousarray(goal4_car, dtype=np.float64)
+        sizes = (C.c_int * 4)()
+        cost = C.c_double(0)
+        self._f("query_commit")(_ptr(w), _ptr(g), C.c_double(vmax), C.c_int(iters), sizes, C.byref(cost))
+        return sizes[0], sizes[1], sizes[2], sizes[3], cost.value
+
+    def best_nodes(self, cap=256):
+        rec = np.zeros((cap, NODE_STRIDE))
+        n = self._f("best_nodes")(_ptr(rec), C.c_int(cap))
+        return rec[:min(n, cap)]
+
+    def best_traj(self, cap_rows=20000, cap_nodes=256):
+        tr = np.zeros((cap_rows, 10))
+        rows = np.zeros(cap_nodes, np.int32)
+        n = self._f("best_traj")(_ptr(tr), C.c_int(cap_rows), _ptr(rows), C.c_int(cap_nodes))
+        return tr[:min(n, cap_rows)], rows
+
     def expand_with(self, samples, heuristic):
         """oracle only: expandTree per sample, sequentially (K=1 semantics), with caller-supplied draws."""
         s = np.ascontiguousarray(samples, dtype=np.float64).reshape(-1, 2)

@@ -7,7 +7,7 @@ Every array is produced by libclrrt_ref_defined.so (reference + the documented U
 cross-checked here against the unmodified libclrrt_ref.so on all untainted rollouts (bit-for-bit); the mask of
 rows where the unmodified build differs is stored as `unmod_differs` and must be a subset of `tainted`.
 Golden sets follow SURVEY.md §8c: G0 known answers, G1 rollouts (C2), G2 candidate lists, G3 whole-query
-replay at K=1, G4 dense-scene verdicts (C3).
+replay at K=1, G4 dense-scene verdicts (C3), G5 receding-horizon loop with carried-over trees (C5).
 """
 import json
 import os
@@ -156,7 +156,41 @@ def g4():
                         obstacles=boxes, parent=par, samples=smp, out=o, unmod_differs=dif)
 
 
+def g5(queries=100, iters=100):
+    """Config C5: consecutive planMotion queries with commit_path = true (tree initialised from the previous best
+    path, rrt/src/rrtplanner.cpp:50-94), moving obstacles, `iters` expandTree calls per query (tests/c5_scenario.py).
+    Per query: the inputs (world state, goal and obstacles in the car frame) and the reference's results."""
+    import c5_scenario as sc
+    ref = CpuPlanner("ref_defined")
+    ref.srand(1)
+    ref.commit_reset()
+    w = np.array([0, 0, 0, 0, 2.0, 0])
+    t = 0.0
+    out = dict(world=[], goal=[], obstacles=[], sizes=[], cost=[], sim_steps=[], nodes=[], n_nodes=[], rows=[])
+    for q in range(queries):
+        goal, obs = sc.to_car_frame(w, sc.world_goal(q), sc.world_obstacles(t))
+        ref.set_obstacles(obs)
+        carried, tree, nbest, steps, cost = ref.query_commit(w, goal, 5.0, iters)
+        assert nbest > 0, f"query {q}: the reference found no path"
+        nodes = ref.best_nodes(16)
+        tr, rows = ref.best_traj()
+        out["world"].append(w.copy()); out["goal"].append(goal); out["obstacles"].append(obs)
+        out["sizes"].append([carried, tree, nbest]); out["cost"].append(cost); out["sim_steps"].append(steps)
+        pad = np.zeros((16, nodes.shape[1])); pad[:len(nodes)] = nodes
+        out["nodes"].append(pad); out["n_nodes"].append(len(nodes)); out["rows"].append(rows[:16].copy())
+        w = sc.advance(w, tr, rows[:nbest])
+        t += sc.DT_QUERY
+    out = {k: np.array(v) for k, v in out.items()}
+    out["iters"] = np.array(iters)
+    print("G5", queries, "queries; carried", out["sizes"][:, 0].min(), "-", out["sizes"][:, 0].max(), "tree",
+          out["sizes"][:, 1].min(), "-", out["sizes"][:, 1].max(), "car x final", out["world"][-1][0])
+    np.savez_compressed(os.path.join(HERE, "g5_replan.npz"), **out)
+
+
 if __name__ == "__main__":
-    g0(); g1_g2(); g3(); g4()
+    if "--only-g5" in sys.argv:
+        g5()
+        sys.exit(0)
+    g0(); g1_g2(); g3(); g4(); g5()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
