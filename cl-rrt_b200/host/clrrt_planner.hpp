@@ -189,18 +189,5 @@ void transformNodesWorldToCar(std::vector<Node>& nodes, const std::vector<double
 
 }  // namespace clrrt
 
-// flat C view of the facade for bindings/tests (same library)
-extern "C" {
-int clrrt_host_plan_motion(const double* car_state6, const double* goal4, double vmax, const clrrt_obstacle* obs,
-                           int n_obs, int samples_per_round, int max_iterations, double budget_ms, unsigned seed,
-                           int device, int* tree_size, int* iterations, clrrt_counters* counters, double* traj8,
-                           int traj_cap, int* traj_len, int32_t* best_ids, int best_cap, int* best_len, double* remat_err);
-// persistent planner: consecutive queries with MotionPlanner::bestNodes carried over (commit_path)
-void* clrrt_host_planner_create(int device, int samples_per_round, int commit_path, int tree_capacity);
-void clrrt_host_planner_destroy(void* h);
-int clrrt_host_planner_query(void* h, const double* world_state6, const double* goal4, double vmax, const clrrt_obstacle* obs,
-                             int n_obs, int max_iterations, double budget_ms, int32_t* sizes4, double* best_cost,
-                             clrrt_counters* counters);
-int clrrt_host_planner_best_nodes(void* h, double* rec20, int cap);
-int clrrt_host_planner_best_traj(void* h, double* traj10, int cap_rows, int32_t* rows_per_node, int cap_nodes);
-}
+// flat C view of the facade for bindings/tests (same library): include/clrrt_host.h
+#include "clrrt_host.h"

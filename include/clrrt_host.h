@@ -1,0 +1,54 @@
+/* clrrt_host.h — C view of the ROS-free host facade (cl-rrt_b200/host, libclrrt_host.so).
+ *
+ * The reference's query-level surface is C++ (MotionPlanner::planMotion / updateObstacles / updateState,
+ * rrt/include/rrt/motionplanner.h:20-42) fed by ROS messages.  The C++ mirror of it lives in
+ * cl-rrt_b200/host/clrrt_planner.hpp; the functions below expose the same calls over plain pointers for bindings and
+ * tests, together with the ROS 1 wire format of the messages involved (car_msgs/msg/*.msg), so that a node can hand
+ * raw message buffers to the planner.  All planning runs on the GPU through include/clrrt.h; there is no CPU path.
+ */
+#ifndef CLRRT_HOST_H
+#define CLRRT_HOST_H
+
+#include "clrrt.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One MotionPlanner::planMotion query from an empty tree (rrt/src/motionplanner.cpp:8-77, commit_path = false).
+ * max_iterations >= 0 replaces Timer(200) by a fixed number of expandTree calls (deterministic); otherwise budget_ms
+ * of wall clock.  seed: srand(seed) before the query (the reference never seeds rand(): 1 reproduces it).
+ * traj8: the published car_msgs/Trajectory after filterMPCmessage, rows x y theta delta v a a_cmd d_cmd. */
+int clrrt_host_plan_motion(const double* car_state6, const double* goal4, double vmax, const clrrt_obstacle* obs,
+                           int n_obs, int samples_per_round, int max_iterations, double budget_ms, unsigned seed,
+                           int device, int* tree_size, int* iterations, clrrt_counters* counters, double* traj8,
+                           int traj_cap, int* traj_len, int32_t* best_ids, int best_cap, int* best_len, double* remat_err);
+
+/* Persistent planner: consecutive queries on one device context with MotionPlanner::bestNodes kept between them
+ * (commit_path != 0: the next tree is initialised from the previous best path, rrt/src/rrtplanner.cpp:50-94). */
+void* clrrt_host_planner_create(int device, int samples_per_round, int commit_path, int tree_capacity);
+void clrrt_host_planner_destroy(void* h);
+/* goal4 and obs in the car frame; sizes4 = {initial tree size, final tree size, best path nodes, expandTree calls} */
+int clrrt_host_planner_query(void* h, const double* world_state6, const double* goal4, double vmax, const clrrt_obstacle* obs,
+                             int n_obs, int max_iterations, double budget_ms, int32_t* sizes4, double* best_cost,
+                             clrrt_counters* counters);
+/* bestNodes of the last query, world frame: {state[10], ref front xy, ref back xy, ref.v.back(), costE, costS, parentID,
+ * goalReached, ref.x.size()} per node; returns the node count */
+int clrrt_host_planner_best_nodes(void* h, double* rec20, int cap);
+/* their trajectories, concatenated rows of 10 state entries; rows_per_node[i] = Node::tra.size(); returns the row count */
+int clrrt_host_planner_best_traj(void* h, double* traj10, int cap_rows, int32_t* rows_per_node, int cap_nodes);
+
+/* ROS 1 wire format (cl-rrt_b200/host/clrrt_wire.hpp): message bytes -> planner inputs, planner outputs -> message bytes.
+ * Parsers return CLRRT_OK (or the element count) and a negative code on truncated / malformed buffers; writers return
+ * the byte count or CLRRT_ERR_CAPACITY. */
+int clrrt_wire_parse_request(const uint8_t* buf, int n, double* goal4, double* vmax, int* bend, int* n_lane_shifts);
+int clrrt_wire_parse_state(const uint8_t* buf, int n, double* state6);
+int clrrt_wire_parse_obstacles(const uint8_t* buf, int n, clrrt_obstacle* out, int cap);
+int clrrt_wire_trajectory(const double* rows8, int n_rows, uint8_t* out, int cap);
+int clrrt_wire_obstacles(const clrrt_obstacle* obs, int n, uint8_t* out, int cap);
+int clrrt_wire_response_roundtrip(const double* rows10, const int32_t* rows_per_segment, int n_segments, uint8_t* out, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

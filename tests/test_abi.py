@@ -24,6 +24,15 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"libclrrt_b200.so does not export {n}"
 
 
+def test_host_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "clrrt_host.h")).read()
+    names = sorted(set(re.findall(r"^(?:int|void\*?)\s+(clrrt_\w+)\s*\(", hdr, flags=re.M)))
+    assert len(names) >= 12
+    lib = C.CDLL(os.path.join(ROOT, "cl-rrt_b200", "libclrrt_host.so"))
+    for n in names:
+        assert hasattr(lib, n), f"libclrrt_host.so does not export {n}"
+
+
 def test_struct_layouts_match_header():
     assert clrrt.NODE_DTYPE.itemsize == 160
     assert clrrt.ROLLOUT_DTYPE.itemsize == 160

@@ -1,5 +1,7 @@
 """Live comparison of the C restatement with the reference's own sources (oracle/_ref, built from
 /root/reference by oracle/build_ref.sh).  Skipped where the reference build is not present."""
+import os
+
 import numpy as np
 import pytest
 
@@ -56,3 +58,25 @@ def test_unmodified_reference_differs_only_when_tainted():
     assert not (differs & (out_d[:, O_TAINT] == 0)).any()
     c2, k2, n2 = o.nearest_batch(s, h)
     assert np.array_equal(n2, cnt) and np.array_equal(k2, key)
+
+
+def test_g5_golden_is_what_the_reference_produces(golden_dir):
+    """The receding-horizon golden (config C5) replayed with the reference build present in this container."""
+    import c5_scenario as sc
+    if not ref_available(True):
+        pytest.skip("oracle/_ref not built (no /root/reference)")
+    g = np.load(os.path.join(golden_dir, "g5_replan.npz"))
+    ref = CpuPlanner("ref_defined")
+    ref.srand(1)
+    ref.commit_reset()
+    w = np.array([0, 0, 0, 0, 2.0, 0])
+    t = 0.0
+    for q in range(12):
+        assert np.allclose(w, g["world"][q], rtol=0, atol=0)
+        goal, obs = sc.to_car_frame(w, sc.world_goal(q), sc.world_obstacles(t))
+        ref.set_obstacles(obs)
+        carried, tree, nbest, steps, cost = ref.query_commit(w, goal, 5.0, int(g["iters"]))
+        assert [carried, tree, nbest] == g["sizes"][q].tolist() and steps == int(g["sim_steps"][q])
+        tr, rows = ref.best_traj()
+        w = sc.advance(w, tr, rows[:nbest])
+        t += sc.DT_QUERY
