@@ -257,6 +257,7 @@ def run_ours(args):
         max_rec = 2 * K_ROUND
         gathered = torch.empty(world * max_rec * rec_bytes, dtype=torch.uint8, device="cuda")
         counts_t = torch.zeros(world, dtype=torch.int32, device="cuda")
+        h_rec = torch.empty(max_rec * rec_bytes, dtype=torch.uint8).pin_memory()
 
     def exchange():
         """per-round node all-gather over NCCL (cl-rrt_b200/exchange.py): per-rank counts, then fixed-stride records;
@@ -292,8 +293,16 @@ def run_ours(args):
         for _ in range(steps):
             st, added = one_round(dev_inputs)
             if download:  # the step's result: the accepted node records, back on the host
-                nodes = pl.tree_download_range(n0, pl.tree_size() - n0)
-                d2h = nodes.nbytes + ctypes.sizeof(clrrt.RoundStats)
+                if world == 1:
+                    nodes = pl.tree_download_range(n0, pl.tree_size() - n0)
+                    d2h = nodes.nbytes + ctypes.sizeof(clrrt.RoundStats)
+                else:
+                    # every rank reads back the records of ITS shard of the round (their union over ranks is the result)
+                    ptr, n_loc = pl.round_records()
+                    nb = n_loc * rec_bytes
+                    if nb:
+                        h_rec[:nb].copy_(_as_cuda_tensor(ptr, max_rec * rec_bytes, local)[:nb])
+                    d2h = nb + ctypes.sizeof(clrrt.RoundStats)
             pl.tree_truncate(n0)
             tot_steps += st.sim_steps
             tot_roll += st.rollouts
