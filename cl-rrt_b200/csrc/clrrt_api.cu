@@ -192,7 +192,7 @@ template <typename R> int configure_launch_t(clrrt_ctx* ctx) {
 }
 
 int configure_launch(clrrt_ctx* ctx) {
-  ctx->smem_bytes = ctx->dprm.static_in_smem ? obstacle_table_bytes(ctx->dprm.n_static) : 0;
+  ctx->smem_bytes = ROLLOUT_SMEM_GB_BYTES + ROLLOUT_SMEM_VB_BYTES + (ctx->dprm.static_in_smem ? obstacle_table_bytes(ctx->dprm.n_static) : 0);
   return ctx->prm.fp32 ? configure_launch_t<float>(ctx) : configure_launch_t<double>(ctx);
 }
 
