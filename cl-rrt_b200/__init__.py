@@ -28,7 +28,8 @@ class Params(C.Structure):
                 ("ctrl_dlavmin", C.c_double), ("ctrl_Kp", C.c_double), ("ctrl_Ki", C.c_double),
                 ("ref_int", C.c_double), ("ref_mindist", C.c_double), ("ref_res", C.c_double), ("vmax", C.c_double),
                 ("ay_road_max", C.c_double), ("Wcost", C.c_double * 5), ("goal", C.c_double * 4),
-                ("obs_use_pred", C.c_int32), ("fp32", C.c_int32)]
+                ("obs_use_pred", C.c_int32), ("fp32", C.c_int32), ("Cxy", C.c_double * 3), ("lane_shift", C.c_double),
+                ("bend", C.c_int32), ("reserved", C.c_int32)]
 
 
 class RoundStats(C.Structure):
@@ -190,6 +191,15 @@ class Planner:
         p.vmax = float(vmax)
         for i in range(4):
             p.goal[i] = float(goal[i])
+        self.set_params()
+
+    def set_road(self, bend, Cxy3=(0.0, 0.0, 0.0), lane_shift=0.0):
+        """MotionRequest.bend / Cxy / laneShifts[0] (rrt/src/motionplanner.cpp:23): lane-deviation cost per sim step."""
+        p = self.params
+        p.bend = 1 if bend else 0
+        for i in range(3):
+            p.Cxy[i] = float(Cxy3[i])
+        p.lane_shift = float(lane_shift)
         self.set_params()
 
     def set_obstacles(self, obstacles):

@@ -160,6 +160,7 @@ void fill_dev_params(clrrt_ctx* ctx) {
   while (ms < (20 / p.sim_dt) && ms < CLRRT_MAX_STEPS_CAP * 64) ms++;  // simulation.cpp:58
   d.max_steps = ms;
   d.obs_use_pred = p.obs_use_pred;
+  d.bend = p.bend ? 1 : 0; d.lane_S = p.lane_shift; d.Cxy1 = p.Cxy[1]; d.Cxy2 = p.Cxy[2];
 }
 
 int upload_params(clrrt_ctx* ctx) {

@@ -92,6 +92,8 @@ struct DevParams {
   // pose grid (x, y, heading mod pi), pose_sub x pose_sub cells per position-grid cell; pose_nh == 0: not built
   int32_t pose_sub, pose_nh;
   int32_t exact_dist;    // 1: return the reference's pseudo-distance (needed when W[2] != 0); 0: verdict only
+  int32_t bend;          // curved-road mode: lane-deviation cost per step (rrt/src/simulation.cpp:92-95)
+  double lane_S, Cxy1, Cxy2;
   float veh_reach;       // half diagonal of the vehicle box (broad phase)
 };
 

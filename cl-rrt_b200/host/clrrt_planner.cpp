@@ -51,8 +51,8 @@ MyRRT::MyRRT(const std::vector<double>& _goalPose, const std::vector<double>& _l
              int tree_capacity, int max_round)
     : bend(_bend), goalPose(_goalPose), laneShifts(_laneShifts), Cxy(_Cxy) {
   if (goalPose.size() < 4) throw Error("goalPose needs 4 entries");
-  if (bend) throw Error("bend=true (curved-road mode) is outside the accelerated path");
   clrrt_default_params(&prm_);
+  setRoad();
   clrrt_vehicle& v = prm_.veh;
   v.dmax = veh.dmax; v.ddmax = veh.ddmax; v.Td = veh.Td; v.Ta = veh.Ta; v.amin = veh.amin; v.amax = veh.amax; v.L = veh.L;
   v.w = veh.w; v.Lrear = veh.Lrear; v.Lfront = veh.Lfront; v.b = veh.b; v.Vch = veh.Vch; v.rho = veh.rho; v.Kus = veh.Kus;
@@ -88,9 +88,20 @@ void MyRRT::addInitialNode(const std::vector<double>& state) {
   n.parent = -1; n.n_ref = N;
   ck(ctx_, clrrt_tree_reset(ctx_, &n, 1), "clrrt_tree_reset");
 }
+void MyRRT::setRoad() {
+  // MotionRequest.bend / Cxy / laneShifts (rrt/src/motionplanner.cpp:23): the lane-deviation cost of simulation.cpp:92-95
+  prm_.bend = bend ? 1 : 0;
+  prm_.lane_shift = 0; prm_.Cxy[0] = prm_.Cxy[1] = prm_.Cxy[2] = 0;
+  if (bend) {
+    if (laneShifts.empty() || Cxy.size() < 3) throw Error("bend=true needs laneShifts[0] and Cxy[0..2]");
+    prm_.lane_shift = laneShifts[0];
+    for (int i = 0; i < 3; i++) prm_.Cxy[i] = Cxy[i];
+  }
+}
 void MyRRT::reconfigure(const std::vector<double>& goal, double vmax, double car_speed, const PlannerParams& prm) {
   if (goal.size() < 4) throw Error("goalPose needs 4 entries");
   goalPose = goal;
+  setRoad();
   prm_.ref_res = std::max(std::abs(car_speed) * prm.ref_int, prm.ref_mindist);  // controller.cpp:18-21
   prm_.vmax = vmax;
   for (int i = 0; i < 5; i++) { prm_.Wcost[i] = prm.Wcost[i]; Wcost[i] = prm.Wcost[i]; }
@@ -144,6 +155,13 @@ double getNodeCost(const MyRRT& RRT, const Vehicle& veh, const double& parentCos
     double Dobs = 100;
     double kappa = tan((*it)[3]) / veh.L;
     cost += RRT.Wcost[0] * (*it)[4] * sim_dt + RRT.Wcost[1] * std::abs(kappa) + RRT.Wcost[2] * exp(-RRT.Wcost[3] * Dobs);
+    if (RRT.bend) {  // d2L, rrt/src/rrtplanner.cpp:98-102
+      const double x = (*it)[0], y = (*it)[1], S = RRT.laneShifts[0];
+      const std::vector<double>& Cxy = RRT.Cxy;
+      double Lx = (x - S * Cxy[1] + y * Cxy[1] - Cxy[1] * Cxy[2]) / (pow(Cxy[1], 2) + 1);
+      double Ly = S + Cxy[2] + (Cxy[1] * (x - S * Cxy[1] + y * Cxy[1] - Cxy[1] * Cxy[2])) / (pow(Cxy[1], 2) + 1);
+      cost += RRT.Wcost[4] * sqrt(pow(Lx - x, 2) + pow(Ly - y, 2));
+    }
   }
   return cost;
 }
@@ -342,7 +360,7 @@ void MotionPlanner::planMotion(MotionRequest req) {
     rrt_ = new MyRRT(req.goal, req.laneShifts, req.Cxy, req.bend, veh, params, req.vmax, carPose[4], device, treeCapacity, round);
     rrt_round_ = round;
   } else {
-    if (req.bend) throw Error("bend=true (curved-road mode) is outside the accelerated path");
+    rrt_->bend = req.bend; rrt_->laneShifts = req.laneShifts; rrt_->Cxy = req.Cxy;
     rrt_->reconfigure(req.goal, req.vmax, carPose[4], params);
   }
   MyRRT& RRT = *rrt_;

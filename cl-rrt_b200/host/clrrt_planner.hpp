@@ -115,6 +115,7 @@ class MyRRT {
   const clrrt_params& params() const { return prm_; }
 
  private:
+  void setRoad();
   clrrt_ctx* ctx_ = nullptr;
   clrrt_params prm_;
   std::vector<Node> carried_;

@@ -51,6 +51,12 @@ typedef struct clrrt_params {
   double goal[4];       /* MyRRT::goalPose = MotionRequest.goal: x, y, heading, v */
   int32_t obs_use_pred; /* rrt/src/rrt_node.cpp:11 */
   int32_t fp32;         /* 0: reference arithmetic (double rollout, float geometry); 1: float rollout */
+  /* curved-road mode (MotionRequest.bend, rrt/src/motionplanner.cpp:23): every sim step adds Wcost[4] x the distance to
+   * the goal lane, getDistToLane(x, y, laneShifts[0], Cxy) (rrt/src/simulation.cpp:49-53, :92-95) */
+  double Cxy[3];        /* MotionRequest.Cxy: road centre line y = Cxy[0] x^2 + Cxy[1] x + Cxy[2] (only [1], [2] are read) */
+  double lane_shift;    /* MotionRequest.laneShifts[0] */
+  int32_t bend;
+  int32_t reserved;
 } clrrt_params;
 
 /* car_msgs/msg/Obstacle2D.msg: vision_msgs/BoundingBox2D obb {center{x,y,theta}, size_x, size_y} + vel.linear */

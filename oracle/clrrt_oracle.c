@@ -56,6 +56,15 @@ static double ref_res, ref_int, ref_mindist, vmax, ay_road_max;
 static int obs_use_pred = 1;
 static int fail_iterlimit, fail_collision, fail_acclimit, sim_count;
 static double Wcost[5];
+/* curved-road mode: MyRRT::bend, laneShifts[0], Cxy (rrt/include/rrt/rrtplanner.h:55-58) */
+static int road_bend = 0;
+static double road_S = 0, road_Cxy[3] = {0, 0, 0};
+/* getDistToLane, rrt/src/simulation.cpp:49-53 */
+static double getDistToLane(double x, double y, double S, const double* Cxy) {
+  double Lx = (x - S * Cxy[1] + y * Cxy[1] - Cxy[1] * Cxy[2]) / (Cxy[1] * Cxy[1] + 1);
+  double Ly = S + Cxy[2] + (Cxy[1] * (x - S * Cxy[1] + y * Cxy[1] - Cxy[1] * Cxy[2])) / (Cxy[1] * Cxy[1] + 1);
+  return sqrt((Lx - x) * (Lx - x) + (Ly - y) * (Ly - y));
+}
 static double goalPose[4];
 static orc_vehicle veh;
 static orc_obstacle* det = NULL;
@@ -401,6 +410,10 @@ static void simulate(const double* state0, orc_ref* ref, int GoalBiased, double 
     out->costE += x[4] * sim_dt; /* :89-91 */
     double kappa = tan(x[3]) / veh.L;
     out->costS += Wcost[0] * x[4] * sim_dt + Wcost[1] * fabs(kappa) + Wcost[2] * exp(-Wcost[3] * Dobs);
+    if (road_bend) { /* rrt/src/simulation.cpp:92-95 */
+      double Dgoallane = getDistToLane(x[0], x[1], road_S, road_Cxy);
+      out->costS += Wcost[4] * Dgoallane;
+    }
     double ay = fabs(x[4] * dx[2]); /* :98-104 */
     if (ay + ay_road_max > 3) { out->endReached = 0; fail_acclimit++; out->fail = 2; i++; goto done; }
     double dist_to_goal = sqrt(sq(x[0] - goalPose[0]) + sq(x[1] - goalPose[1])); /* :110-111 */
@@ -692,6 +705,10 @@ void orc_init(void) {
 }
 void orc_set_tie_mode(int m) { tie_mode = m; }
 void orc_set_weights(const double* w5) { memcpy(Wcost, w5, sizeof Wcost); }
+/* MotionRequest.bend / laneShifts[0] / Cxy, rrt/src/motionplanner.cpp:23 */
+void orc_set_road(int bend, const double* Cxy3, double lane_shift) {
+  road_bend = bend; road_S = lane_shift; memcpy(road_Cxy, Cxy3, sizeof road_Cxy);
+}
 void orc_get_vehicle(double* v14) { memcpy(v14, &veh, sizeof veh); }
 void orc_srand(unsigned seed) { srand(seed); }
 void orc_set_obstacles(const double* o7, int n) {

@@ -103,6 +103,8 @@ Vehicle g_veh;
 MyRRT* g_rrt = nullptr;
 vector<car_msgs::Obstacle2D> g_obstacles;
 vector<double> g_goal{50, 0, 0, 0};
+bool g_bend = false;                       // MotionRequest.bend / laneShifts / Cxy (rrt/src/motionplanner.cpp:23)
+vector<double> g_laneShifts{0}, g_Cxy;
 
 void set_launch_params() {
   // rrt/launch/parameters.launch:3-20
@@ -197,6 +199,11 @@ void ref_set_weights(const double* w5) {
   ros::param::set("motionplanner/weight_obstacle_slope", w5[3]);
   ros::param::set("motionplanner/weight_lanedeviation", w5[4]);
 }
+void ref_set_road(int bend, const double* Cxy3, double lane_shift) {
+  g_bend = bend != 0;
+  g_laneShifts.assign(1, lane_shift);
+  g_Cxy.assign(Cxy3, Cxy3 + 3);
+}
 void ref_get_vehicle(double* v14) {
   const double a[14] = {g_veh.dmax, g_veh.ddmax, g_veh.Td, g_veh.Ta, g_veh.amin, g_veh.amax, g_veh.L,
                         g_veh.w, g_veh.Lrear, g_veh.Lfront, g_veh.b, g_veh.Vch, g_veh.rho, g_veh.Kus};
@@ -235,8 +242,7 @@ void ref_tree_init(const double* car_state6, const double* goal4, double vmax_) 
   vmax = vmax_;
   vgoal = goal4[3];
   delete g_rrt;
-  vector<double> laneShifts{0}, Cxy;
-  g_rrt = new MyRRT(g_goal, laneShifts, Cxy, false);
+  g_rrt = new MyRRT(g_goal, g_laneShifts, g_Cxy, g_bend);
   g_rrt->det = g_obstacles;
   g_rrt->carState = carPose;
   g_carState = carPose;

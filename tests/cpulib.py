@@ -74,6 +74,12 @@ class CpuPlanner:
         obs = np.ascontiguousarray(obs, dtype=np.float64).reshape(-1, 7)
         self._f("set_obstacles")(_ptr(obs), C.c_int(len(obs)))
 
+    def set_road(self, bend, Cxy3=(0, 0, 0), lane_shift=0.0):
+        """MotionRequest.bend / Cxy / laneShifts[0]: the lane-deviation cost of the curved-road mode (takes effect at
+        the next tree_init for the reference libraries)."""
+        c = np.ascontiguousarray(Cxy3, dtype=np.float64)
+        self._f("set_road")(C.c_int(int(bend)), _ptr(c), C.c_double(lane_shift))
+
     def set_tie_mode(self, mode):
         """oracle only: 0 = equal keys ordered by node id (the product's rule), 1 = libstdc++ std::sort order."""
         self._f("set_tie_mode")(C.c_int(mode))

@@ -7,7 +7,7 @@ Every array is produced by libclrrt_ref_defined.so (reference + the documented U
 cross-checked here against the unmodified libclrrt_ref.so on all untainted rollouts (bit-for-bit); the mask of
 rows where the unmodified build differs is stored as `unmod_differs` and must be a subset of `tainted`.
 Golden sets follow SURVEY.md §8c: G0 known answers, G1 rollouts (C2), G2 candidate lists, G3 whole-query
-replay at K=1, G4 dense-scene verdicts (C3), G5 receding-horizon loop with carried-over trees (C5).
+replay at K=1, G4 dense-scene verdicts (C3), G5 receding-horizon loop with carried-over trees (C5), G6 curved-road cost (bend).
 """
 import json
 import os
@@ -156,6 +156,32 @@ def g4():
                         obstacles=boxes, parent=par, samples=smp, out=o, unmod_differs=dif)
 
 
+def g6():
+    """Curved-road mode (MotionRequest.bend = true): the same rollouts as G1's obstacle scene with the
+    lane-deviation cost of rrt/src/simulation.cpp:92-95 switched on (getDistToLane with laneShifts[0], Cxy)."""
+    g1 = np.load(os.path.join(HERE, "g1_rollouts.npz"))
+    Cxy, shift = (0.001, 0.02, 0.5), 1.5
+    outs = []
+    for kind in ("ref_defined", "ref"):
+        p = CpuPlanner(kind)
+        p.set_obstacles(g1["obstacles"])
+        p.set_road(True, Cxy, shift)
+        p.srand(1)
+        p.tree_init(g1["car"], g1["goal"], 5.0)
+        p.tree_import(g1["tree"])
+        outs.append(p.rollout_batch(g1["parent"], g1["samples"], np.zeros(len(g1["parent"]), np.uint8)))
+        p.set_road(False)
+    d, u = outs
+    differs = (d != u).any(axis=1) & ~(np.isnan(d) & np.isnan(u)).all(axis=1)
+    assert not (differs & ~(d[:, O_TAINT] != 0)).any()
+    base = g1["out_obs"]
+    same_state = np.array_equal(d[:, :10], base[:, :10])
+    print("G6 rollouts", len(d), "states equal to G1:", same_state, "mean extra costS", float(np.nanmean(d[:, 11] - base[:, 11])))
+    assert same_state and (d[:, 11] >= base[:, 11]).all()
+    np.savez_compressed(os.path.join(HERE, "g6_bend.npz"), Cxy=np.array(Cxy), lane_shift=np.array(shift), out=d,
+                        unmod_differs=differs)
+
+
 def g5(queries=100, iters=100):
     """Config C5: consecutive planMotion queries with commit_path = true (tree initialised from the previous best
     path, rrt/src/rrtplanner.cpp:50-94), moving obstacles, `iters` expandTree calls per query (tests/c5_scenario.py).
@@ -191,6 +217,9 @@ if __name__ == "__main__":
     if "--only-g5" in sys.argv:
         g5()
         sys.exit(0)
-    g0(); g1_g2(); g3(); g4(); g5()
+    if "--only-g6" in sys.argv:
+        g6()
+        sys.exit(0)
+    g0(); g1_g2(); g3(); g4(); g5(); g6()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

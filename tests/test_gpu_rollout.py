@@ -40,6 +40,22 @@ def test_g1_rollouts_vs_reference_golden(clrrt, planner, g1, name):
     print(f"tainted fraction {tainted.mean():.3f}")
 
 
+def test_g6_curved_road_cost(clrrt, planner, g1, golden_dir):
+    """bend = true: the lane-deviation term of rrt/src/simulation.cpp:92-95 in every step's cost; states and
+    verdicts are those of G1, costS carries the extra term (golden G6 from the reference's sources)."""
+    g6 = np.load(os.path.join(golden_dir, "g6_bend.npz"))
+    planner.set_query(g1["car"], g1["goal"], 5.0)
+    planner.set_road(True, g6["Cxy"], float(g6["lane_shift"]))
+    try:
+        planner.tree_reset_records(g1["tree"])
+        planner.set_obstacles(g1["obstacles"])
+        got = clrrt.rollouts_as_table(planner.propagate_batch(g1["parent"], g1["samples"]))
+        assert_rollouts_match(got, g6["out"], "G6 bend")
+        assert (got[:, 11] >= g1["out_obs"][:, 11]).all() and (got[:, 11] > g1["out_obs"][:, 11]).mean() > 0.9
+    finally:
+        planner.set_road(False)
+
+
 @pytest.mark.parametrize("name", ["obs", "live"])
 def test_g1_goal_biased_rollouts(clrrt, planner, g1, name):
     """Goal-biased references duplicate their junction point (rrt/src/reference.cpp:56-63): for the one or two steps

@@ -59,6 +59,21 @@ def test_g1_rollouts(orc, golden_dir, name):
     assert not (g[f"unmod_differs_{name}"] & (g[f"out_{name}"][:, O_TAINT] == 0)).any()
 
 
+def test_g6_curved_road_cost(orc, golden_dir):
+    """bend = true: getDistToLane in every step's cost (rrt/src/simulation.cpp:49-53, :92-95), bit for bit."""
+    g = np.load(os.path.join(golden_dir, "g1_rollouts.npz"))
+    g6 = np.load(os.path.join(golden_dir, "g6_bend.npz"))
+    orc.set_obstacles(g["obstacles"])
+    orc.set_road(True, g6["Cxy"], float(g6["lane_shift"]))
+    try:
+        orc.tree_init(g["car"], g["goal"], 5.0)
+        orc.tree_import(g["tree"])
+        out = orc.rollout_batch(g["parent"], g["samples"])
+        assert same(out, g6["out"])
+    finally:
+        orc.set_road(False)
+
+
 def test_g2_candidate_lists(orc, golden_dir):
     g = np.load(os.path.join(golden_dir, "g2_nearest.npz"))
     orc.set_obstacles(scene_c1_boxes())
