@@ -58,6 +58,8 @@ struct clrrt_ctx {
   int32_t *d_cand = nullptr, *d_count = nullptr, *d_valid = nullptr;
   int32_t *d_order = nullptr, *d_hist = nullptr;  // launch order of the (sample, rank) pairs; (rank, length bucket) histogram
   uint32_t* d_done = nullptr;
+  void* d_init = nullptr;            // prepared rollouts of a round (setup_kernel) + per-thread scratch records
+  size_t init_stride = 0;
   uint8_t* d_bucket = nullptr;
   int32_t *d_best = nullptr, *d_slot = nullptr;
   uint8_t* d_res_code = nullptr;
@@ -282,6 +284,8 @@ int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_r
   ok &= mal((void**)&ctx->d_hist, 1024 * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_done, K * sizeof(uint32_t));
   ok &= mal((void**)&ctx->d_bucket, K * CLRRT_SORT_LIMIT);
+  ctx->init_stride = ((K * CLRRT_SORT_LIMIT + (size_t)ctx->num_sms * 4 * ROLLOUT_THREADS) + 31) & ~(size_t)31;
+  ok &= mal(&ctx->d_init, ctx->init_stride * LANE_INIT_BYTES_PER_RECORD);
   ok &= mal((void**)&ctx->d_best, K * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_slot, K * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_res_code, K * CLRRT_SORT_LIMIT);
@@ -310,7 +314,7 @@ int clrrt_destroy(clrrt_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->tree_mem, ctx->stage_mem, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells, ctx->d_bnd, ctx->d_hot, ctx->d_best, ctx->d_res_code, ctx->d_res_steps, ctx->d_slot, ctx->d_ref_end, ctx->d_cold, ctx->d_mov, ctx->d_samples, ctx->d_heur,
-                  ctx->d_cand, ctx->d_key, ctx->d_count, ctx->d_valid, ctx->d_order, ctx->d_hist, ctx->d_done, ctx->d_bucket, ctx->d_ints, ctx->d_block_sums,
+                  ctx->d_cand, ctx->d_key, ctx->d_count, ctx->d_valid, ctx->d_order, ctx->d_hist, ctx->d_done, ctx->d_bucket, ctx->d_init, ctx->d_ints, ctx->d_block_sums,
                   ctx->d_records, ctx->d_counters, ctx->batch.d_parent, ctx->batch.d_gb,
                   ctx->batch.d_samples, ctx->batch.d_out, ctx->batch.d_traj, ctx->batch.d_ref};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -760,6 +764,10 @@ int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint
   job.best_rank = ctx->d_best; job.done_mask = ctx->d_done; job.res_code = ctx->d_res_code; job.res_steps = ctx->d_res_steps;
   job.out_nodes = ctx->stage; job.out_valid = ctx->d_valid;
   job.counters = ctx->d_counters; job.refill_min = ctx->refill_min; job.phase_clk = ctx->d_counters + 8;
+  job.init = ctx->d_init; job.init_stride = ctx->init_stride;
+  if (ctx->prm.fp32) setup_kernel<float><<<(n_pairs + 127) / 128, 128, 0, st>>>(job);
+  else setup_kernel<double><<<(n_pairs + 127) / 128, 128, 0, st>>>(job);
+  CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev[5], st));
   if ((rc = launch_rollout(ctx, job, n_pairs))) return rc;
   CK(cudaEventRecord(ctx->ev[2], st));
