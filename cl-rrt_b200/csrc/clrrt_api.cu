@@ -61,7 +61,7 @@ struct clrrt_ctx {
   void* d_init = nullptr;            // prepared rollouts of a round (setup_kernel) + per-thread scratch records
   size_t init_stride = 0;
   uint8_t* d_bucket = nullptr;
-  int32_t *d_best = nullptr, *d_slot = nullptr;
+  int32_t* d_slot = nullptr;
   uint8_t* d_res_code = nullptr;
   uint16_t* d_res_steps = nullptr;
   double* d_ref_end = nullptr;
@@ -210,7 +210,7 @@ template <typename R, bool ROUND> int launch_rollout_t(clrrt_ctx* ctx, const Rol
 }
 
 int launch_rollout(clrrt_ctx* ctx, const RolloutJob& job, int n_items_hint) {
-  const bool round = job.best_rank != nullptr;
+  const bool round = job.sample_word != nullptr;
   int per_sm = round ? ctx->blocks_per_sm_main : ctx->blocks_per_sm_gb;
   if (ctx->blocks_override > 0) per_sm = std::min(per_sm, ctx->blocks_override);
   const int lanes_per_block = ROLLOUT_THREADS;
@@ -286,7 +286,6 @@ int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_r
   ok &= mal((void**)&ctx->d_bucket, K * CLRRT_SORT_LIMIT);
   ctx->init_stride = ((K * CLRRT_SORT_LIMIT + (size_t)ctx->num_sms * 4 * ROLLOUT_THREADS) + 31) & ~(size_t)31;
   ok &= mal(&ctx->d_init, ctx->init_stride * LANE_INIT_BYTES_PER_RECORD);
-  ok &= mal((void**)&ctx->d_best, K * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_slot, K * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_res_code, K * CLRRT_SORT_LIMIT);
   ok &= mal((void**)&ctx->d_res_steps, K * CLRRT_SORT_LIMIT * sizeof(uint16_t));
@@ -313,7 +312,7 @@ int clrrt_destroy(clrrt_ctx* ctx) {
   if (!ctx) return CLRRT_ERR_ARG;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  void* ptrs[] = {ctx->tree_mem, ctx->stage_mem, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells, ctx->d_bnd, ctx->d_hot, ctx->d_best, ctx->d_res_code, ctx->d_res_steps, ctx->d_slot, ctx->d_ref_end, ctx->d_cold, ctx->d_mov, ctx->d_samples, ctx->d_heur,
+  void* ptrs[] = {ctx->tree_mem, ctx->stage_mem, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells, ctx->d_bnd, ctx->d_hot, ctx->d_res_code, ctx->d_res_steps, ctx->d_slot, ctx->d_ref_end, ctx->d_cold, ctx->d_mov, ctx->d_samples, ctx->d_heur,
                   ctx->d_cand, ctx->d_key, ctx->d_count, ctx->d_valid, ctx->d_order, ctx->d_hist, ctx->d_done, ctx->d_bucket, ctx->d_init, ctx->d_ints, ctx->d_block_sums,
                   ctx->d_records, ctx->d_counters, ctx->batch.d_parent, ctx->batch.d_gb,
                   ctx->batch.d_samples, ctx->batch.d_out, ctx->batch.d_traj, ctx->batch.d_ref};
@@ -746,7 +745,6 @@ int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint
   //    that resolved the sample (rollout.cuh)
   const int n_pairs = K * CLRRT_SORT_LIMIT;
   CK(cudaMemsetAsync(ctx->d_ints, 0, 4 * sizeof(int32_t), st));
-  CK(cudaMemsetAsync(ctx->d_best, 0x7f, (size_t)K * sizeof(int32_t), st));
   CK(cudaMemsetAsync(ctx->d_done, 0, (size_t)K * sizeof(uint32_t), st));
   CK(cudaMemsetAsync(ctx->d_valid + K, 0, (size_t)K * sizeof(int32_t), st));
   CK(cudaMemsetAsync(ctx->d_hist, 0, 1024 * sizeof(int32_t), st));
@@ -761,7 +759,7 @@ int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint
   job.n_samples = K; job.n_ranks = CLRRT_SORT_LIMIT; job.n_items = n_pairs; job.n_items_dev = ctx->d_ints + 2;
   job.head = ctx->d_ints + 0; job.cand = ctx->d_cand; job.count = ctx->d_count; job.order = ctx->d_order;
   job.cand_stride = CLRRT_SORT_LIMIT; job.sample_xy = d_sample_xy; job.parents = ctx->tree; job.ref_end = ctx->d_ref_end;
-  job.best_rank = ctx->d_best; job.done_mask = ctx->d_done; job.res_code = ctx->d_res_code; job.res_steps = ctx->d_res_steps;
+  job.sample_word = ctx->d_done; job.res_code = ctx->d_res_code; job.res_steps = ctx->d_res_steps;
   job.out_nodes = ctx->stage; job.out_valid = ctx->d_valid;
   job.counters = ctx->d_counters; job.refill_min = ctx->refill_min; job.phase_clk = ctx->d_counters + 8;
   job.init = ctx->d_init; job.init_stride = ctx->init_stride;
@@ -772,7 +770,7 @@ int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint
   if ((rc = launch_rollout(ctx, job, n_pairs))) return rc;
   CK(cudaEventRecord(ctx->ev[2], st));
   SelectArgs sa;
-  sa.K = K; sa.n_ranks = CLRRT_SORT_LIMIT; sa.count = ctx->d_count; sa.best_rank = ctx->d_best;
+  sa.K = K; sa.n_ranks = CLRRT_SORT_LIMIT; sa.count = ctx->d_count; sa.sample_word = ctx->d_done;
   sa.res_code = ctx->d_res_code; sa.res_steps = ctx->d_res_steps; sa.valid = ctx->d_valid;
   sa.slot = ctx->d_slot; sa.counters = ctx->d_counters;
   select_kernel<<<(K + 255) / 256, 256, 0, st>>>(sa);
