@@ -95,6 +95,7 @@ def load_library():
     lib.clrrt_append_records.argtypes = [vp, vp, vp, ip, ip]
     lib.clrrt_set_tuning.argtypes = [vp, ip, ip]
     lib.clrrt_set_grid_cell.argtypes = [vp, dp]
+    lib.clrrt_set_nearest_mode.argtypes = [vp, ip]
     lib.clrrt_tree_download_range.argtypes = [vp, ip, ip, vp]
     lib.clrrt_draw_samples.argtypes = [vp, ip, vp, vp]
     lib.srand = C.CDLL(None).srand
@@ -208,6 +209,9 @@ class Planner:
 
     def set_tuning(self, refill_min=8, blocks_per_sm=0):
         self._ck(self.lib.clrrt_set_tuning(self.h, refill_min, blocks_per_sm))
+
+    def set_nearest_mode(self, mode):
+        self._ck(self.lib.clrrt_set_nearest_mode(self.h, int(mode)))
 
     def set_grid_cell(self, metres):
         self._ck(self.lib.clrrt_set_grid_cell(self.h, float(metres)))

@@ -49,6 +49,7 @@ struct clrrt_ctx {
   size_t pose_cap = 0;
   double grid_cell = 1.0;            // requested cell size in metres (clrrt_set_grid_cell)
   bool pose_enabled = true;          // clrrt_set_grid_cell with a negative size disables the pose grid (tests)
+  int nn_mode = 0;                   // candidate search: 0 = choose by size, 1 = always the sorted search, 2 = never
   int pose_sub_max = 2;              // pose cells per position cell and axis (measured on C3: 1 -> 5.84, 2 -> 4.98, 4 -> 4.88 ms per round at 4x the table)
   ObsCold* d_cold = nullptr;
   ObsMoving* d_mov = nullptr;
@@ -59,6 +60,10 @@ struct clrrt_ctx {
   int32_t *d_cand = nullptr, *d_count = nullptr, *d_valid = nullptr;
   int32_t *d_order = nullptr, *d_hist = nullptr;  // launch order of the (sample, rank) pairs; (rank, length bucket) histogram
   uint32_t* d_done = nullptr;
+  // candidate search: nodes and samples sorted along the goal bearing (nearest.cuh)
+  void* nn_mem = nullptr;
+  NNSortArgs nn{};
+  float *d_tile_ulo = nullptr, *d_tile_uhi = nullptr, *d_tile_ce = nullptr;
   void* d_init = nullptr;            // prepared rollouts of a round (setup_kernel) + per-thread scratch records
   size_t init_stride = 0;
   uint8_t* d_bucket = nullptr;
@@ -285,6 +290,28 @@ int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_r
   ok &= mal((void**)&ctx->d_hist, 1024 * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_done, K * sizeof(uint32_t));
   ok &= mal((void**)&ctx->d_bucket, K * CLRRT_SORT_LIMIT);
+  {
+    const size_t n8 = ((size_t)tree_capacity + 7) & ~(size_t)7, k8 = (K + 7) & ~(size_t)7;
+    const size_t bytes = n8 * (7 * 8 + 3 * 4 + 4 + 4) + (n8 + k8) * 4 + k8 * 4 + 3 * NN_BINS * 4 + 3 * (n8 / NEAREST_TILE + 8) * 4 + 1024;
+    ok &= mal(&ctx->nn_mem, bytes);
+    if (ok) {
+      unsigned char* p = reinterpret_cast<unsigned char*>(ctx->nn_mem);
+      auto take = [&](size_t nbytes) { unsigned char* q = p; p += (nbytes + 15) & ~(size_t)15; return q; };
+      NNSortArgs& s = ctx->nn;
+      double** dd[] = {&s.nx, &s.ny, &s.rbx, &s.rby, &s.dpx, &s.dpy, &s.ang};
+      for (auto d : dd) *d = reinterpret_cast<double*>(take(n8 * 8));
+      float** ff[] = {&s.ca, &s.sa, &s.ce};
+      for (auto f : ff) *f = reinterpret_cast<float*>(take(n8 * 4));
+      s.node_id = reinterpret_cast<int32_t*>(take(n8 * 4));
+      s.sbin = reinterpret_cast<int32_t*>(take(n8 * 4));
+      s.bin = reinterpret_cast<int32_t*>(take((n8 + k8) * 4));
+      s.sample_id = reinterpret_cast<int32_t*>(take(k8 * 4));
+      s.hist = reinterpret_cast<int32_t*>(take(3 * NN_BINS * 4));
+      ctx->d_tile_ce = reinterpret_cast<float*>(take((n8 / NEAREST_TILE + 8) * 4));
+      ctx->d_tile_ulo = reinterpret_cast<float*>(take((n8 / NEAREST_TILE + 8) * 4));
+      ctx->d_tile_uhi = reinterpret_cast<float*>(take((n8 / NEAREST_TILE + 8) * 4));
+    }
+  }
   ctx->init_stride = ((K * CLRRT_SORT_LIMIT + (size_t)ctx->num_sms * 4 * ROLLOUT_THREADS) + 31) & ~(size_t)31;
   ok &= mal(&ctx->d_init, ctx->init_stride * LANE_INIT_BYTES_PER_RECORD);
   ok &= mal((void**)&ctx->d_slot, K * sizeof(int32_t));
@@ -314,7 +341,7 @@ int clrrt_destroy(clrrt_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->tree_mem, ctx->stage_mem, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells, ctx->d_bnd, ctx->d_hot, ctx->d_res_code, ctx->d_res_steps, ctx->d_slot, ctx->d_ref_end, ctx->d_cold, ctx->d_mov, ctx->d_samples, ctx->d_heur,
-                  ctx->d_cand, ctx->d_key, ctx->d_count, ctx->d_valid, ctx->d_order, ctx->d_hist, ctx->d_done, ctx->d_bucket, ctx->d_init, ctx->d_ints, ctx->d_block_sums,
+                  ctx->d_cand, ctx->d_key, ctx->d_count, ctx->d_valid, ctx->d_order, ctx->d_hist, ctx->d_done, ctx->d_bucket, ctx->d_init, ctx->nn_mem, ctx->d_ints, ctx->d_block_sums,
                   ctx->d_records, ctx->d_counters, ctx->batch.d_parent, ctx->batch.d_gb,
                   ctx->batch.d_samples, ctx->batch.d_out, ctx->batch.d_traj, ctx->batch.d_ref};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -629,11 +656,44 @@ int clrrt_draw_samples(const double goal[4], int K, double* sample_xy, uint8_t* 
 
 static int nearest_dev(clrrt_ctx* ctx, const double* d_samples, const uint8_t* d_heur, int K, int32_t* d_cand,
                        float* d_key, int32_t* d_count) {
+  const bool sorted = ctx->nn_mode == 1 || (ctx->nn_mode == 0 && (double)K * (double)ctx->n_tree >= NN_SORT_MIN_PAIRS);
+  if (!sorted) {
+    NearestArgs a;
+    memset(&a, 0, sizeof a);
+    a.sample_xy = d_samples; a.heuristic = d_heur; a.K = K; a.n_nodes = ctx->n_tree; a.tree = ctx->tree;
+    a.cand = d_cand; a.key = d_key; a.count = d_count; a.feas_len = ctx->dprm.feas_len;
+    nearest_topk_kernel<<<(K + NEAREST_WARPS - 1) / NEAREST_WARPS, NEAREST_THREADS, 0, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    return CLRRT_OK;
+  }
+  // 1. sort nodes and samples along the axis of the sampling box (goal bearing, rrtplanner.cpp:188-197): counting sort
+  //    over NN_BINS bins covering [-15 m, dGoal + 25 m] (everything outside lands in the end bins)
+  cudaStream_t st = ctx->stream;
+  NNSortArgs& s = ctx->nn;
+  const double gx = ctx->prm.goal[0], gy = ctx->prm.goal[1];
+  const double beta = std::atan2(gy, gx), dgoal = std::sqrt(gx * gx + gy * gy);
+  s.tree = ctx->tree; s.n_nodes = ctx->n_tree; s.K = K; s.sample_xy = d_samples; s.heuristic = d_heur;
+  s.cb = (float)std::cos(beta); s.sb = (float)std::sin(beta);
+  s.u0 = -15.0f;
+  const float bin_w = (float)((dgoal + 40.0) / NN_BINS);
+  s.inv_bin = 1.0f / bin_w;
+  const int n_el = ctx->n_tree + K, n_tiles = (ctx->n_tree + NEAREST_TILE - 1) / NEAREST_TILE;
+  CK(cudaMemsetAsync(s.hist, 0, 3 * NN_BINS * sizeof(int32_t), st));
+  nn_bin_kernel<<<(n_el + 255) / 256, 256, 0, st>>>(s);
+  nn_scan_kernel<<<2, NN_BINS, 0, st>>>(s.hist);
+  nn_scatter_kernel<<<(n_el + 255) / 256, 256, 0, st>>>(s);
+  nn_tile_kernel<<<n_tiles, NEAREST_TILE, 0, st>>>(s.sbin, s.ce, ctx->n_tree, s.u0, bin_w, ctx->d_tile_ulo, ctx->d_tile_uhi, ctx->d_tile_ce);
+  CK(cudaGetLastError());
+  // 2. the search
   NearestArgs a;
   a.sample_xy = d_samples; a.heuristic = d_heur; a.K = K; a.n_nodes = ctx->n_tree; a.tree = ctx->tree;
   a.cand = d_cand; a.key = d_key; a.count = d_count; a.feas_len = ctx->dprm.feas_len;
+  a.so.n_nodes = ctx->n_tree; a.so.n_tiles = n_tiles; a.so.node_id = s.node_id;
+  a.so.nx = s.nx; a.so.ny = s.ny; a.so.rbx = s.rbx; a.so.rby = s.rby; a.so.dpx = s.dpx; a.so.dpy = s.dpy; a.so.ang = s.ang;
+  a.so.ca = s.ca; a.so.sa = s.sa; a.so.ce = s.ce; a.so.tile_ulo = ctx->d_tile_ulo; a.so.tile_uhi = ctx->d_tile_uhi; a.so.tile_ce = ctx->d_tile_ce;
+  a.so.sample_id = s.sample_id; a.so.cb = s.cb; a.so.sb = s.sb;
   const int blocks = (K + NEAREST_WARPS - 1) / NEAREST_WARPS;
-  nearest_topk_kernel<<<blocks, NEAREST_THREADS, 0, ctx->stream>>>(a);
+  nearest_sorted_kernel<<<blocks, NEAREST_THREADS, 0, ctx->stream>>>(a);
   CK(cudaGetLastError());
   return CLRRT_OK;
 }
@@ -858,6 +918,12 @@ int clrrt_set_tuning(clrrt_ctx* ctx, int refill_min, int blocks_per_sm) {
   if (!ctx || refill_min < 1 || refill_min > 32 || blocks_per_sm < 0) return CLRRT_ERR_ARG;
   ctx->refill_min = refill_min;
   ctx->blocks_override = blocks_per_sm;
+  return CLRRT_OK;
+}
+
+int clrrt_set_nearest_mode(clrrt_ctx* ctx, int mode) {
+  if (!ctx || mode < 0 || mode > 2) return CLRRT_ERR_ARG;
+  ctx->nn_mode = mode;
   return CLRRT_OK;
 }
 

@@ -197,6 +197,9 @@ int clrrt_set_tuning(clrrt_ctx* ctx, int refill_min, int blocks_per_sm);
  * half of it), applied at the next clrrt_set_obstacles; a negative size disables the pose grid, leaving the position
  * grid path only.  Results do not depend on it. */
 int clrrt_set_grid_cell(clrrt_ctx* ctx, double metres);
+/* Candidate search: 0 = pick by problem size (default), 1 = always sort nodes and samples along the goal bearing first,
+ * 2 = never.  Results do not depend on it. */
+int clrrt_set_nearest_mode(clrrt_ctx* ctx, int mode);
 
 #ifdef __cplusplus
 }

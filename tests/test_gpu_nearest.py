@@ -21,13 +21,18 @@ def ulp_diff(a, b):
     return np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64))
 
 
+@pytest.mark.parametrize("mode", [2, 1])  # storage-order search / nodes and samples sorted along the goal bearing first
 @pytest.mark.parametrize("N", [1, 64, 250, 1500])
-def test_g2_candidate_lists(clrrt, planner, golden_dir, N):
+def test_g2_candidate_lists(clrrt, planner, golden_dir, N, mode):
     g = np.load(os.path.join(golden_dir, "g2_nearest.npz"))
     car, goal = (0, 0, 0, 0, 3, 0), (50, 0, 0, 0)
     planner.set_query(car, goal, 5.0)
     planner.tree_reset_records(g["tree"][:N])
-    cand, key, cnt = planner.nearest_batch(g["samples"], g["heuristic"])
+    planner.set_nearest_mode(mode)
+    try:
+        cand, key, cnt = planner.nearest_batch(g["samples"], g["heuristic"])
+    finally:
+        planner.set_nearest_mode(0)
     assert np.array_equal(cnt, g[f"count_{N}"])
     # keys: bit-exact with the reference's float libm
     assert np.array_equal(key, g[f"key_{N}"]), f"max ulp diff {ulp_diff(key, g[f'key_{N}']).max()}"
@@ -62,8 +67,22 @@ def test_large_snapshot_vs_oracle(clrrt, planner):
     planner.tree_truncate(4096)
     tree = planner.tree_download_records()
     orc.tree_import(tree)
-    cand, key, cnt = planner.nearest_batch(s, h)
     oc, ok, on = orc.nearest_batch(s, h)
-    assert np.array_equal(cnt, on)
-    assert np.array_equal(key, ok)
-    assert np.array_equal(cand, oc)
+    for mode in (2, 1, 0):
+        planner.set_nearest_mode(mode)
+        cand, key, cnt = planner.nearest_batch(s, h)
+        assert np.array_equal(cnt, on)
+        assert np.array_equal(key, ok)
+        assert np.array_equal(cand, oc)
+    # a goal off the x axis: the sort axis follows the goal bearing
+    goal2 = (40, 25, 0.5, 0)
+    planner.set_query(car, goal2, 5.0)
+    planner.tree_reset_records(tree)
+    orc.tree_init(car, goal2, 5.0)
+    orc.tree_import(tree)
+    oc, ok, on = orc.nearest_batch(s, h)
+    for mode in (2, 1):
+        planner.set_nearest_mode(mode)
+        cand, key, cnt = planner.nearest_batch(s, h)
+        assert np.array_equal(cnt, on) and np.array_equal(key, ok) and np.array_equal(cand, oc)
+    planner.set_nearest_mode(0)
