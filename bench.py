@@ -250,6 +250,8 @@ def run_ours(args):
     h_smp = torch.from_numpy(smp).pin_memory()
     h_heu = torch.from_numpy(heu).pin_memory()
     np_smp, np_heu = h_smp.numpy(), h_heu.numpy()  # views of the pinned buffers
+    h_nodes = torch.empty(2 * K_ROUND * clrrt.RECORD_BYTES, dtype=torch.uint8).pin_memory()
+    np_nodes = h_nodes.numpy().view(clrrt.NODE_DTYPE)  # pinned destination of the e2e leg's result read-back
     if world > 1:
         from clrrt_b200.exchange import gather_records
         pl.set_defer_append(True)
@@ -294,7 +296,7 @@ def run_ours(args):
             st, added = one_round(dev_inputs)
             if download:  # the step's result: the accepted node records, back on the host
                 if world == 1:
-                    nodes = pl.tree_download_range(n0, pl.tree_size() - n0)
+                    nodes = pl.tree_download_range(n0, pl.tree_size() - n0, out=np_nodes)
                     d2h = nodes.nbytes + ctypes.sizeof(clrrt.RoundStats)
                 else:
                     # every rank reads back the records of ITS shard of the round (their union over ranks is the result)
@@ -307,9 +309,10 @@ def run_ours(args):
             tot_steps += st.sim_steps
             tot_roll += st.rollouts
             ms_roll += st.ms_rollout
-            # nearest_topk, ref_end, order_scan, order_scatter, rollout, select, scan_block_sums, scan_sums, pack_records,
-            # append_records (single GPU: appended inside the round; multi GPU: one append per rank chunk)
-            launches += 10 if world == 1 else 9 + world
+            # nn_bin, nn_scan, nn_scatter, nn_tile, nearest_sorted, ref_end, order_scan, order_scatter, setup, rollout, select,
+            # scan_block_sums, scan_sums, pack_records, append_records (single GPU: appended inside the round; multi GPU:
+            # one append per rank chunk); the e2e leg adds export_nodes for the read-back
+            launches += 15 if world == 1 else 14 + world
         e1.record(stream)
         if world > 1:
             dist.barrier()

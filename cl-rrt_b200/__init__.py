@@ -249,8 +249,9 @@ class Planner:
         self._ck(self.lib.clrrt_tree_download(self.h, out.ctypes.data, n, C.byref(got)))
         return out[:got.value]
 
-    def tree_download_range(self, first, count):
-        out = np.zeros(count, NODE_DTYPE)
+    def tree_download_range(self, first, count, out=None):
+        """`out`: optional caller buffer (e.g. a view of pinned memory) of at least `count` NODE_DTYPE records."""
+        out = np.zeros(count, NODE_DTYPE) if out is None else out[:count]
         self._ck(self.lib.clrrt_tree_download_range(self.h, first, count, out.ctypes.data))
         return out
 

@@ -64,6 +64,8 @@ struct clrrt_ctx {
   void* nn_mem = nullptr;
   NNSortArgs nn{};
   float *d_tile_ulo = nullptr, *d_tile_uhi = nullptr, *d_tile_ce = nullptr;
+  NodeRecord* d_export = nullptr;    // staging of clrrt_tree_download_range
+  size_t export_cap = 0;
   void* d_init = nullptr;            // prepared rollouts of a round (setup_kernel) + per-thread scratch records
   size_t init_stride = 0;
   uint8_t* d_bucket = nullptr;
@@ -341,7 +343,7 @@ int clrrt_destroy(clrrt_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->tree_mem, ctx->stage_mem, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells, ctx->d_bnd, ctx->d_hot, ctx->d_res_code, ctx->d_res_steps, ctx->d_slot, ctx->d_ref_end, ctx->d_cold, ctx->d_mov, ctx->d_samples, ctx->d_heur,
-                  ctx->d_cand, ctx->d_key, ctx->d_count, ctx->d_valid, ctx->d_order, ctx->d_hist, ctx->d_done, ctx->d_bucket, ctx->d_init, ctx->nn_mem, ctx->d_ints, ctx->d_block_sums,
+                  ctx->d_cand, ctx->d_key, ctx->d_count, ctx->d_valid, ctx->d_order, ctx->d_hist, ctx->d_done, ctx->d_bucket, ctx->d_init, ctx->nn_mem, ctx->d_export, ctx->d_ints, ctx->d_block_sums,
                   ctx->d_records, ctx->d_counters, ctx->batch.d_parent, ctx->batch.d_gb,
                   ctx->batch.d_samples, ctx->batch.d_out, ctx->batch.d_traj, ctx->batch.d_ref};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -600,31 +602,19 @@ int clrrt_tree_download_range(clrrt_ctx* ctx, int first, int n, clrrt_node* host
   if (!ctx || !host || first < 0 || n < 0 || first + n > ctx->n_tree) return CLRRT_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   if (n == 0) return CLRRT_OK;
-  std::vector<double> d((size_t)n * 17);
-  std::vector<float> f((size_t)n * 2);
-  std::vector<int32_t> q((size_t)n * 4);
-  const double* dsrc[17] = {ctx->tree.x, ctx->tree.y, ctx->tree.th, ctx->tree.de, ctx->tree.v, ctx->tree.a, ctx->tree.t,
-                            ctx->tree.s7, ctx->tree.s8, ctx->tree.s9, ctx->tree.rfx, ctx->tree.rfy, ctx->tree.rbx,
-                            ctx->tree.rby, ctx->tree.vback, ctx->tree.smx, ctx->tree.smy};
-  cudaStream_t st = ctx->stream;
-  for (int k = 0; k < 17; k++) CK(cudaMemcpyAsync(d.data() + (size_t)k * n, dsrc[k] + first, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(f.data(), ctx->tree.costE + first, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(f.data() + n, ctx->tree.costS + first, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(q.data(), ctx->tree.parent + first, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(q.data() + n, ctx->tree.goal + first, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(q.data() + 2 * (size_t)n, ctx->tree.nref + first, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(q.data() + 3 * (size_t)n, ctx->tree.kind + first, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  for (int i = 0; i < n; i++) {
-    clrrt_node& o = host[i];
-    for (int k = 0; k < 10; k++) o.state[k] = d[(size_t)k * n + i];
-    o.ref_front[0] = d[(size_t)10 * n + i]; o.ref_front[1] = d[(size_t)11 * n + i];
-    o.ref_back[0] = d[(size_t)12 * n + i]; o.ref_back[1] = d[(size_t)13 * n + i];
-    o.ref_vback = d[(size_t)14 * n + i];
-    o.costE = f[i]; o.costS = f[(size_t)n + i];
-    o.parent = q[i]; o.goal_reached = q[(size_t)n + i]; o.n_ref = q[2 * (size_t)n + i]; o.kind = q[3 * (size_t)n + i];
-    o.sample[0] = d[(size_t)15 * n + i]; o.sample[1] = d[(size_t)16 * n + i];
+  static_assert(sizeof(clrrt_node) == sizeof(NodeRecord), "clrrt_node and NodeRecord share one layout");
+  if ((size_t)n > ctx->export_cap) {
+    if (ctx->d_export) cudaFree(ctx->d_export);
+    ctx->d_export = nullptr;
+    ctx->export_cap = 0;
+    const size_t cap = std::max<size_t>((size_t)n, 1024) * 2;
+    CK(cudaMalloc((void**)&ctx->d_export, cap * sizeof(NodeRecord)));
+    ctx->export_cap = cap;
   }
+  export_nodes_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->tree, first, n, ctx->d_export);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(host, ctx->d_export, (size_t)n * sizeof(NodeRecord), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return CLRRT_OK;
 }
 

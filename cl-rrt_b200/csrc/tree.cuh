@@ -128,6 +128,22 @@ __global__ void append_records_kernel(NodeSoA t, int first, const NodeRecord* __
 }
 
 // extractBestPath, rrtplanner.cpp:318-368: arg-min of float costS over goal-flagged nodes (first minimum wins)
+// tree nodes [first, first + n) -> clrrt_node records (same 160-byte layout as NodeRecord, parents as tree indices):
+// one coalesced device-to-host copy instead of one per field
+__global__ void __launch_bounds__(256) export_nodes_kernel(NodeSoA t, int first, int n, NodeRecord* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int g = first + i;
+  NodeRecord r;
+  r.state[0] = t.x[g]; r.state[1] = t.y[g]; r.state[2] = t.th[g]; r.state[3] = t.de[g]; r.state[4] = t.v[g];
+  r.state[5] = t.a[g]; r.state[6] = t.t[g]; r.state[7] = t.s7[g]; r.state[8] = t.s8[g]; r.state[9] = t.s9[g];
+  r.rf[0] = t.rfx[g]; r.rf[1] = t.rfy[g]; r.rb[0] = t.rbx[g]; r.rb[1] = t.rby[g];
+  r.vback = t.vback[g]; r.costE = t.costE[g]; r.costS = t.costS[g];
+  r.parent = t.parent[g]; r.goal = t.goal[g]; r.nref = t.nref[g]; r.kind = t.kind[g];
+  r.smp[0] = t.smx[g]; r.smp[1] = t.smy[g];
+  out[i] = r;
+}
+
 __global__ void __launch_bounds__(1024) best_goal_kernel(NodeSoA t, int n, int32_t* best_id) {
   __shared__ float s_c[32];
   __shared__ int s_i[32];
