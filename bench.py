@@ -234,6 +234,8 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
     torch.cuda.set_device(local)
+    # nvidia-smi needs about a second before its first sample: start it before the workload is built
+    sampler = ClockSampler(local) if rank == 0 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # a dedicated (non-default) stream shared by torch and the library: torch.cuda.Event then times the library's kernels
@@ -326,7 +328,6 @@ def run_ours(args):
             ms, tot_steps, tot_roll = float(tmax[0]), int(t[1]), int(t[2])
         return ms, tot_steps, tot_roll, ms_roll, launches, d2h, st
 
-    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         one_round(True)
         pl.tree_truncate(n0)
