@@ -37,7 +37,7 @@ want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct"]
 with open(os.path.join(out, f"{tag}_rollout_kernel_ncu.md"), "w") as f:
     f.write(f"# ncu --set full ({tag}): candidate search and rollout kernel of one C3 round (65536 samples, 1000 obstacles, 4096-node tree)\n\n"
-            "`ncu --set full --clock-control none --import-source on -k 'regex:rollout_kernel|nearest_topk_kernel' -s 6 -c 2 python bench.py --steps 2 --warmup 1 --no-cpu-baseline`\n\n")
+            "`ncu --set full --clock-control none --import-source on -k 'regex:rollout_kernel|nearest_sorted_kernel' -s 6 -c 2 python bench.py --steps 2 --warmup 1 --no-cpu-baseline`\n\n")
     cols = [i for i in range(2, len(r))]
     f.write("| metric | unit | " + " | ".join(f"launch {i-2}" for i in cols) + " |\n|---|---|" + "---|" * len(cols) + "\n")
     for w in want:
