@@ -35,6 +35,25 @@ GOAL = (100.0, 0.0, 0.0, 0.0)
 VMAX = 5.0
 
 
+SCALING = "weak"
+SCENE = "c3"
+
+
+def select_workload(name, world):
+    """--workload c4: 2^20 samples per round IN TOTAL, sharded over the ranks (strong scaling),
+    the 10 boxes of C1/C2, goal 50 m ahead, 4096-node tree snapshot.  Default c3: 65 536 samples per round and GPU."""
+    global WORKLOAD, K_ROUND, CAR, GOAL, SCALING, SCENE
+    if name == "c4":
+        K_ROUND = (1 << 20) // world
+        CAR, GOAL, SCALING, SCENE = (0.0, 0.0, 0.0, 0.0, 3.0, 0.0), (50.0, 0.0, 0.0, 0.0), "strong", "c4"
+        WORKLOAD = (f"C4 multi-GPU sweep: 2^20 samples/round in total ({K_ROUND} per GPU), 10 OBB obstacles, "
+                    "4096-node tree snapshot, fp64 parity mode")
+
+
+def scene_boxes():
+    return scene_c3_boxes() if SCENE == "c3" else scene_c1_boxes()
+
+
 def scene_c3_boxes():
     """closed-form layout, no RNG."""
     o = np.zeros((1000, 7))
@@ -98,7 +117,7 @@ class ClockSampler:
 
 def build_workload(pl, clrrt, rank, world):
     """Scene, tree snapshot (grown on the GPU with this library, deterministic) and the per-rank sample shards."""
-    boxes = scene_c3_boxes()
+    boxes = scene_boxes()
     pl.set_query(CAR, GOAL, VMAX)
     pl.set_obstacles(boxes)
     pl.tree_reset(clrrt.root_node(CAR))
@@ -367,7 +386,7 @@ def run_ours(args):
         peaks = {"hbm_gbs": 6650.0}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": SCALING, "vs_baseline": None,
         "dtype": ("f32 rollout (tolerance mode) + f32 SAT/Dubins" if args.fp32 else "f64 rollout + f32 SAT/Dubins (the reference's mixture)"),
         "data": "synthetic",
         "config": {"workload": WORKLOAD if not args.fp32 else WORKLOAD.replace("fp64 parity mode", "fp32 mode"), "samples_per_round_per_gpu": K_ROUND, "tree_nodes": n0, "obstacles": n_obs,
@@ -438,7 +457,7 @@ def run_reference(args):
     import multiprocessing as mp
     from cpulib import CpuPlanner, ref_available
     kind = "ref_defined" if ref_available(True) else "oracle"
-    boxes = scene_c3_boxes()
+    boxes = scene_boxes()
     # the same tree snapshot needs the GPU library; without a GPU grow a smaller one with the CPU code itself
     tree = None
     try:
@@ -496,8 +515,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4"], help="c3 (default): the headline single-GPU configuration, weak "
+                    "scaling; c4: 2^20 samples per round in total, strong scaling")
     ap.add_argument("--fp32", action="store_true", help="fp32 rollout mode (tolerance mode; default is the fp64 parity mode)")
     args = ap.parse_args()
+    select_workload(args.workload, int(os.environ.get("WORLD_SIZE", "1")))
     if args.impl == "reference":
         run_reference(args)
     else:
