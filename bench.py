@@ -146,11 +146,11 @@ def scene_c1_boxes():
     return o
 
 
-def query_200ms_ours(clrrt, device, K=4096, budget_ms=200.0):
+def query_200ms_ours(clrrt, device, K=16384, budget_ms=200.0):
     """Second half of BASELINE.json's metric: tree nodes grown by one planMotion query with a 200 ms expansion budget
     (config C1).  Samples are drawn on the host with the reference's expressions (rand() after srand(1)), K per round;
     the wall clock covers drawing, the host->device copy and the round."""
-    pl = clrrt.Planner(device=device, tree_capacity=(1 << 20) + 2 * K, max_round=K)
+    pl = clrrt.Planner(device=device, tree_capacity=(1 << 20) + 2 * K, max_round=K)  # K: 1024 -> 50 k nodes, 4096 -> 113 k, 16384 -> 225 k, 65536 -> 305 k (8 rounds)
     pl.set_query(C1_CAR, C1_GOAL, VMAX)
     pl.set_obstacles(scene_c1_boxes())
     pl.tree_reset(clrrt.root_node(C1_CAR))
