@@ -78,6 +78,7 @@ struct clrrt_ctx {
   int32_t* d_block_sums = nullptr;
   NodeRecord* d_records = nullptr;
   unsigned long long* d_counters = nullptr;  // 8
+  unsigned long long* d_timeline = nullptr;  // CLRRT_PHASE_CLOCKS builds: 3 words per staging slot (rollout.cuh)
   int32_t* h_ints = nullptr;                 // pinned
   unsigned long long* h_counters = nullptr;  // pinned
   RolloutScratch batch;
@@ -324,6 +325,9 @@ int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_r
   ok &= mal((void**)&ctx->d_block_sums, ((K + SCAN_THREADS - 1) / SCAN_THREADS + 1) * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_records, 2 * K * sizeof(NodeRecord));
   ok &= mal((void**)&ctx->d_counters, 32 * sizeof(unsigned long long));
+#ifdef CLRRT_PHASE_CLOCKS
+  ok &= mal((void**)&ctx->d_timeline, (K * CLRRT_SORT_LIMIT + K) * 3 * sizeof(unsigned long long));
+#endif
   ok &= cudaMallocHost((void**)&ctx->h_ints, 16 * sizeof(int32_t)) == cudaSuccess;
   ok &= cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(unsigned long long)) == cudaSuccess;
   if (!ok) { ctx->err = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()); return fail(CLRRT_ERR_CUDA); }
@@ -344,7 +348,7 @@ int clrrt_destroy(clrrt_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->tree_mem, ctx->stage_mem, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells, ctx->d_bnd, ctx->d_hot, ctx->d_res_code, ctx->d_res_steps, ctx->d_slot, ctx->d_ref_end, ctx->d_cold, ctx->d_mov, ctx->d_samples, ctx->d_heur,
                   ctx->d_cand, ctx->d_key, ctx->d_count, ctx->d_valid, ctx->d_order, ctx->d_hist, ctx->d_done, ctx->d_bucket, ctx->d_init, ctx->nn_mem, ctx->d_export, ctx->d_ints, ctx->d_block_sums,
-                  ctx->d_records, ctx->d_counters, ctx->batch.d_parent, ctx->batch.d_gb,
+                  ctx->d_records, ctx->d_counters, ctx->d_timeline, ctx->batch.d_parent, ctx->batch.d_gb,
                   ctx->batch.d_samples, ctx->batch.d_out, ctx->batch.d_traj, ctx->batch.d_ref};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->h_ints) cudaFreeHost(ctx->h_ints);
@@ -420,6 +424,15 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
       m.ohh = h / 2; m.ohw = w / 2; m.oc = co; m.os = so; m.pad0 = m.pad1 = m.pad2 = 0;
       mov.push_back(m);
     }
+  }
+  // margins of the verdict-only check (rollout.cuh, box_class): proportional to the largest |coordinate| an obstacle of
+  // this scene is tested at (moving obstacles: rollout.cuh widens the margin with the lane's own position)
+  {
+    double maxabs = 0;
+    for (int i = 0; i < n; i++)
+      maxabs = std::max(maxabs, std::max(std::fabs(host[i].cx), std::fabs(host[i].cy)) + std::fabs(host[i].size_x) + std::fabs(host[i].size_y) + 2.0 * vreach + 1.0);
+    ctx->dprm.fine_margin = std::max(FINE_MARGIN_MIN, FINE_MARGIN_REL * (float)(2.0 * maxabs));
+    ctx->dprm.deep_margin = DEEP_MARGIN_FACTOR * ctx->dprm.fine_margin;
   }
   if (st.size() > 32000 || mov.size() > 32000) { ctx->err = "more than 32000 static or moving obstacles"; return CLRRT_ERR_CAPACITY; }
   // Z-order sort of the static obstacles so that 32 consecutive ones form a compact group (the verdict does not
@@ -548,7 +561,7 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
       const float infl = (float)(cell_f * M_SQRT1_2 + 0.01 + 2.0 * vreach * std::sin((dth / 2 + 1e-3) / 2));
       build_pose_grid_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(
           ctx->d_bnd, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells, ns, gnx, gny, sub, nh, (float)cell_f, infl,
-          ctx->dprm.veh_hh, ctx->dprm.veh_hw);
+          ctx->dprm.veh_hh, ctx->dprm.veh_hw, ctx->dprm.fine_margin);
       CK(cudaGetLastError());
       CK(cudaStreamSynchronize(ctx->stream));
       ctx->dprm.pose_sub = sub; ctx->dprm.pose_nh = nh;
@@ -814,6 +827,10 @@ int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint
   job.out_nodes = ctx->stage; job.out_valid = ctx->d_valid;
   job.counters = ctx->d_counters; job.refill_min = ctx->refill_min; job.phase_clk = ctx->d_counters + 8;
   job.init = ctx->d_init; job.init_stride = ctx->init_stride;
+#ifdef CLRRT_PHASE_CLOCKS
+  job.timeline = ctx->d_timeline;
+  CK(cudaMemsetAsync(ctx->d_timeline, 0, ((size_t)ctx->max_round * (CLRRT_SORT_LIMIT + 1)) * 3 * sizeof(unsigned long long), st));
+#endif
   if (ctx->prm.fp32) setup_kernel<float><<<(n_pairs + 127) / 128, 128, 0, st>>>(job);
   else setup_kernel<double><<<(n_pairs + 127) / 128, 128, 0, st>>>(job);
   CK(cudaGetLastError());
@@ -930,6 +947,16 @@ int clrrt_debug_phase_clocks(clrrt_ctx* ctx, unsigned long long out[16], int res
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaMemcpy(out, ctx->d_counters + 8, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   if (reset) CK(cudaMemset(ctx->d_counters + 8, 0, 16 * sizeof(unsigned long long)));
+  return CLRRT_OK;
+}
+
+// diagnostic builds (-DCLRRT_PHASE_CLOCKS) only: start/end/steps of every rollout of the last round, 3 words per staging slot
+int clrrt_debug_timeline(clrrt_ctx* ctx, unsigned long long* out, int K) {
+  if (!ctx || !out || K < 1 || K > ctx->max_round) return CLRRT_ERR_ARG;
+  if (!ctx->d_timeline) return CLRRT_ERR_STATE;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(out, ctx->d_timeline, (size_t)K * (CLRRT_SORT_LIMIT + 1) * 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return CLRRT_OK;
 }
 

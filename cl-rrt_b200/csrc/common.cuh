@@ -95,6 +95,10 @@ struct DevParams {
   int32_t bend;          // curved-road mode: lane-deviation cost per step (rrt/src/simulation.cpp:92-95)
   double lane_S, Cxy1, Cxy2;
   float veh_reach;       // half diagonal of the vehicle box (broad phase)
+  // verdict-only collision check (rollout.cuh, warp_collide): a gap above fine_margin along one of the four box directions
+  // is a gap the reference's float SAT sees; an overlap above deep_margin along all four is an intersection it sees; only
+  // pairs in between run the reference's SAT.  Both scale with the scene's coordinates (clrrt_set_obstacles).
+  float fine_margin, deep_margin;
 };
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
