@@ -94,6 +94,9 @@ def load_library():
     lib.clrrt_round_records.argtypes = [vp, C.POINTER(vp), C.POINTER(ip)]
     lib.clrrt_append_records.argtypes = [vp, vp, vp, ip, ip]
     lib.clrrt_set_tuning.argtypes = [vp, ip, ip]
+    lib.clrrt_set_tie_mode.argtypes = [vp, ip]
+    lib.clrrt_tie_sorts.argtypes = [vp]
+    lib.clrrt_tie_sorts.restype = C.c_longlong
     lib.clrrt_set_grid_cell.argtypes = [vp, dp]
     lib.clrrt_set_nearest_mode.argtypes = [vp, ip]
     lib.clrrt_tree_download_range.argtypes = [vp, ip, ip, vp]
@@ -206,6 +209,13 @@ class Planner:
     def set_obstacles(self, obstacles):
         o = np.ascontiguousarray(obstacles, dtype=np.float64).reshape(-1, 7)
         self._ck(self.lib.clrrt_set_obstacles(self.h, o.ctypes.data if len(o) else None, len(o)))
+
+    def set_tie_mode(self, mode=1):
+        """1 (default): K = 1 searches order equal keys as the reference's std::sort does; 0: lower node id first."""
+        self._ck(self.lib.clrrt_set_tie_mode(self.h, mode))
+
+    def tie_sorts(self):
+        return int(self.lib.clrrt_tie_sorts(self.h))
 
     def set_tuning(self, refill_min=8, blocks_per_sm=0):
         self._ck(self.lib.clrrt_set_tuning(self.h, refill_min, blocks_per_sm))

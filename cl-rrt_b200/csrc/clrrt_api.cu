@@ -78,6 +78,10 @@ struct clrrt_ctx {
   int32_t* d_block_sums = nullptr;
   NodeRecord* d_records = nullptr;
   unsigned long long* d_counters = nullptr;  // 8
+  // K = 1: the reference's order of equal keys (nearest_reference_ties)
+  float* d_all_key = nullptr; uint8_t* d_all_feas = nullptr;
+  int tie_mode = 1;          // 1: std::sort's order of equal keys for single-sample searches; 0: lower node id everywhere
+  long long tie_sorts = 0;   // searches that had to repeat the reference's sort on the host
   unsigned long long* d_timeline = nullptr;  // CLRRT_PHASE_CLOCKS builds: 3 words per staging slot (rollout.cuh)
   int32_t* h_ints = nullptr;                 // pinned
   unsigned long long* h_counters = nullptr;  // pinned
@@ -325,6 +329,8 @@ int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_r
   ok &= mal((void**)&ctx->d_block_sums, ((K + SCAN_THREADS - 1) / SCAN_THREADS + 1) * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_records, 2 * K * sizeof(NodeRecord));
   ok &= mal((void**)&ctx->d_counters, 32 * sizeof(unsigned long long));
+  ok &= mal((void**)&ctx->d_all_key, (size_t)tree_capacity * sizeof(float));
+  ok &= mal((void**)&ctx->d_all_feas, (size_t)tree_capacity);
 #ifdef CLRRT_PHASE_CLOCKS
   ok &= mal((void**)&ctx->d_timeline, (K * CLRRT_SORT_LIMIT + K) * 3 * sizeof(unsigned long long));
 #endif
@@ -348,7 +354,7 @@ int clrrt_destroy(clrrt_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->tree_mem, ctx->stage_mem, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells, ctx->d_bnd, ctx->d_hot, ctx->d_res_code, ctx->d_res_steps, ctx->d_slot, ctx->d_ref_end, ctx->d_cold, ctx->d_mov, ctx->d_samples, ctx->d_heur,
                   ctx->d_cand, ctx->d_key, ctx->d_count, ctx->d_valid, ctx->d_order, ctx->d_hist, ctx->d_done, ctx->d_bucket, ctx->d_init, ctx->nn_mem, ctx->d_export, ctx->d_ints, ctx->d_block_sums,
-                  ctx->d_records, ctx->d_counters, ctx->d_timeline, ctx->batch.d_parent, ctx->batch.d_gb,
+                  ctx->d_records, ctx->d_counters, ctx->d_timeline, ctx->d_all_key, ctx->d_all_feas, ctx->batch.d_parent, ctx->batch.d_gb,
                   ctx->batch.d_samples, ctx->batch.d_out, ctx->batch.d_traj, ctx->batch.d_ref};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->h_ints) cudaFreeHost(ctx->h_ints);
@@ -657,9 +663,51 @@ int clrrt_draw_samples(const double goal[4], int K, double* sample_xy, uint8_t* 
   return CLRRT_OK;
 }
 
+// K = 1 with the reference's order of equal keys (nearest.cuh, tie_check_kernel): when the list found on the device
+// depends on how equal keys are ordered, repeat the reference's std::sort call (rrtplanner.cpp:233, :256) — the same
+// libstdc++ routine on the same (node id, key) pairs in the same initial order — and walk the result as upstream does.
+static int nearest_reference_ties(clrrt_ctx* ctx, const double* d_samples, const uint8_t* d_heur, int32_t* d_cand, float* d_key,
+                                  int32_t* d_count) {
+  cudaStream_t st = ctx->stream;
+  const int n = ctx->n_tree;
+  TieArgs t;
+  t.tree = ctx->tree; t.n_nodes = n; t.sample_xy = d_samples; t.heuristic = d_heur; t.feas_len = ctx->dprm.feas_len;
+  t.cand = d_cand; t.key = d_key; t.count = d_count; t.all_key = ctx->d_all_key; t.all_feas = ctx->d_all_feas; t.flag = ctx->d_ints + 6;
+  CK(cudaMemsetAsync(ctx->d_ints + 6, 0, sizeof(int32_t), st));
+  tie_check_kernel<<<(n + 127) / 128, 128, 0, st>>>(t);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->h_ints + 6, ctx->d_ints + 6, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (ctx->h_ints[6] == 0) return CLRRT_OK;
+  ctx->tie_sorts++;
+  std::vector<float> key((size_t)n);
+  std::vector<uint8_t> feas((size_t)n);
+  CK(cudaMemcpyAsync(key.data(), ctx->d_all_key, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(feas.data(), ctx->d_all_feas, (size_t)n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  std::vector<std::pair<int, float>> dVector;
+  for (int nodeid = 0; nodeid != n; nodeid++) dVector.push_back(std::make_pair(nodeid, key[(size_t)nodeid]));
+  std::sort(dVector.begin(), dVector.end(), [](const std::pair<int, float>& a, const std::pair<int, float>& b) { return a.second < b.second; });
+  int32_t cand[CLRRT_SORT_LIMIT];
+  float ckey[CLRRT_SORT_LIMIT];
+  int32_t cnt = 0;
+  for (int r = 0; r < CLRRT_SORT_LIMIT; r++) { cand[r] = -1; ckey[r] = 0.0f; }
+  for (const auto& e : dVector) {
+    if (feas[(size_t)e.first]) { cand[cnt] = e.first; ckey[cnt] = e.second; cnt++; }
+    if (cnt == CLRRT_SORT_LIMIT) break;
+  }
+  CK(cudaMemcpyAsync(d_cand, cand, sizeof cand, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_key, ckey, sizeof ckey, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_count, &cnt, sizeof cnt, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));  // the sources are on this stack frame
+  return CLRRT_OK;
+}
+
 static int nearest_dev(clrrt_ctx* ctx, const double* d_samples, const uint8_t* d_heur, int K, int32_t* d_cand,
                        float* d_key, int32_t* d_count) {
   const bool sorted = ctx->nn_mode == 1 || (ctx->nn_mode == 0 && (double)K * (double)ctx->n_tree >= NN_SORT_MIN_PAIRS);
+  const bool ref_ties = K == 1 && ctx->tie_mode == 1;
+  if (ref_ties && !d_key) d_key = ctx->d_key;
   if (!sorted) {
     NearestArgs a;
     memset(&a, 0, sizeof a);
@@ -667,6 +715,7 @@ static int nearest_dev(clrrt_ctx* ctx, const double* d_samples, const uint8_t* d
     a.cand = d_cand; a.key = d_key; a.count = d_count; a.feas_len = ctx->dprm.feas_len;
     nearest_topk_kernel<<<(K + NEAREST_WARPS - 1) / NEAREST_WARPS, NEAREST_THREADS, 0, ctx->stream>>>(a);
     CK(cudaGetLastError());
+    if (ref_ties) return nearest_reference_ties(ctx, d_samples, d_heur, d_cand, d_key, d_count);
     return CLRRT_OK;
   }
   // 1. sort nodes and samples along the axis of the sampling box (goal bearing, rrtplanner.cpp:188-197): counting sort
@@ -698,6 +747,7 @@ static int nearest_dev(clrrt_ctx* ctx, const double* d_samples, const uint8_t* d
   const int blocks = (K + NEAREST_WARPS - 1) / NEAREST_WARPS;
   nearest_sorted_kernel<<<blocks, NEAREST_THREADS, 0, ctx->stream>>>(a);
   CK(cudaGetLastError());
+  if (ref_ties) return nearest_reference_ties(ctx, d_samples, d_heur, d_cand, d_key, d_count);
   return CLRRT_OK;
 }
 
@@ -927,6 +977,13 @@ int clrrt_set_tuning(clrrt_ctx* ctx, int refill_min, int blocks_per_sm) {
   ctx->blocks_override = blocks_per_sm;
   return CLRRT_OK;
 }
+
+int clrrt_set_tie_mode(clrrt_ctx* ctx, int mode) {
+  if (!ctx || mode < 0 || mode > 1) return CLRRT_ERR_ARG;
+  ctx->tie_mode = mode;
+  return CLRRT_OK;
+}
+long long clrrt_tie_sorts(const clrrt_ctx* ctx) { return ctx ? ctx->tie_sorts : -1; }
 
 int clrrt_set_nearest_mode(clrrt_ctx* ctx, int mode) {
   if (!ctx || mode < 0 || mode > 2) return CLRRT_ERR_ARG;

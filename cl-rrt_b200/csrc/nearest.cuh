@@ -483,6 +483,45 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_topk_kernel(const Nea
   if (lane == 0) a.count[j] = cnt;
 }
 
+// ---- K = 1, the reference's own sequential algorithm: the order of EQUAL keys ----------------------------------------
+// The reference sorts (node id, key) pairs with std::sort on the key alone (rrtplanner.cpp:233, :256): the order of equal
+// keys is whatever libstdc++'s unstable introsort leaves, and it decides which of two equally ranked parents is tried
+// first (seen in the receding-horizon loop, where carried-over nodes produce exactly equal keys).  The kernels above order
+// equal keys by node id.  For a single sample this kernel evaluates key and feasibility of EVERY node and raises a flag
+// when a feasible node outside the list position it would take shares its key with a list entry (or a feasible key is
+// NaN); the host then repeats the reference's very std::sort call on the downloaded keys (clrrt_api.cu, nearest_dev).
+struct TieArgs {
+  NodeSoA tree;
+  int32_t n_nodes;
+  const double* sample_xy;
+  const uint8_t* heuristic;
+  double feas_len;
+  const int32_t* cand;   // [10] the list found with the node-id tie rule
+  const float* key;      // [10]
+  const int32_t* count;  // [1]
+  float* all_key;        // [n_nodes]
+  uint8_t* all_feas;     // [n_nodes]
+  int32_t* flag;
+};
+__global__ void __launch_bounds__(128) tie_check_kernel(const TieArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n_nodes) return;
+  const double sx = a.sample_xy[0], sy = a.sample_xy[1];
+  const bool optimize = a.heuristic[0] != 0;
+  float key = dubins_key(sx, sy, a.tree.x[i], a.tree.y[i], a.tree.ca[i], a.tree.sa[i]);
+  if (optimize) key = a.tree.costE[i] + key;  // rrtplanner.cpp:254
+  const double rbx = a.tree.rbx[i], rby = a.tree.rby[i];
+  const bool feas = feasible_node(sx, sy, rbx, rby, rbx - a.tree.rfx[i], rby - a.tree.rfy[i], a.tree.angPar[i], a.feas_len);
+  a.all_key[i] = key;
+  a.all_feas[i] = feas ? 1 : 0;
+  if (!feas) return;
+  bool tie = !(key == key);
+  const int cnt = a.count[0];
+  for (int r = 0; r < cnt; r++)
+    if (key == a.key[r] && a.cand[r] != i) tie = true;
+  if (tie) atomicOr(a.flag, 1);
+}
+
 // Per-node quantities the search reads: cosf/sinf of ang = (float)(-theta) (rrtplanner.cpp:378-380) and the heading
 // of the node's own reference (rrtplanner.cpp:273).
 __global__ void derive_nodes_kernel(NodeSoA t, int first, int n) {

@@ -193,6 +193,14 @@ int clrrt_get_device(const clrrt_ctx* ctx);
 /* Launch tuning of the rollout kernel: refill_min = idle lanes a warp accumulates before it fetches new work
  * (default 8; 1 = refill immediately); blocks_per_sm = resident blocks of the persistent grid (0 = occupancy maximum). */
 int clrrt_set_tuning(clrrt_ctx* ctx, int refill_min, int blocks_per_sm);
+/* Order of EQUAL keys in the candidate list.  The reference sorts (node id, key) pairs with std::sort on the key alone
+ * (rrt/src/rrtplanner.cpp:233, :256), so equal keys end up in whatever order libstdc++'s introsort leaves them.
+ * mode 1 (default): single-sample searches (K = 1, the reference's own sequential algorithm) reproduce that order — when,
+ * and only when, a feasible node shares its key with a list entry the search repeats the reference's std::sort call on
+ * the host; mode 0: lower node id first everywhere (what batched searches, K > 1, always do).
+ * clrrt_tie_sorts: how many searches of this context took the host route. */
+int clrrt_set_tie_mode(clrrt_ctx* ctx, int mode);
+long long clrrt_tie_sorts(const clrrt_ctx* ctx);
 /* Broad-phase grids of the collision check: cell size of the position grid in metres (default 1; the pose grid uses
  * half of it), applied at the next clrrt_set_obstacles; a negative size disables the pose grid, leaving the position
  * grid path only.  Results do not depend on it. */

@@ -57,31 +57,65 @@ class HostPlanner:
             self.h = None
 
 
+# The first query of G5 in which a goal-biased rollout crosses the duplicated junction point of its reference with the
+# 3-point window straddling the pair: the reference's Lagrange interpolation then divides
+# by ~1e-15, the saturated steer command is +-dmax with a sign that hangs on the last bit of glibc's sin/cos/tan, and the
+# device's libm differs from glibc in that bit.  The product's rollout there ends 2 steps later; every query before it is
+# bit-for-bit the reference's.
+FIRST_JUNCTION_NOISE_QUERY = 50
+
+
 def test_receding_horizon_loop_matches_reference(golden_dir):
     g = np.load(os.path.join(golden_dir, "g5_replan.npz"))
     iters = int(g["iters"])
-    n_queries = 40  # of the 100 recorded: ~2 ms per K=1 expandTree call on the GPU
+    n_queries = int(g["world"].shape[0])  # config C5: all 100 recorded queries (~2 ms per K=1 expandTree call on the GPU)
     hp = HostPlanner(samples_per_round=1, commit_path=True)
     C.CDLL(None).srand(C.c_uint(1))  # the reference never seeds rand(); its stream continues across queries
     worst = 0.0
+    exact = 0
     for q in range(n_queries):
         sizes, cost, cnt = hp.query(g["world"][q], g["goal"][q], g["obstacles"][q], iters)
         want = g["sizes"][q]
-        assert sizes[:3].tolist() == want.tolist(), f"query {q}: carried/tree/best {sizes[:3]} vs reference {want}"
-        assert sizes[3] == iters and cnt.sim_count == int(g["sim_steps"][q]), f"query {q}: sim steps"
         nodes = hp.best_nodes()
         ref_nodes = g["nodes"][q][:int(g["n_nodes"][q])]
+        same = (sizes[:3].tolist() == want.tolist() and cnt.sim_count == int(g["sim_steps"][q]) and len(nodes) == len(ref_nodes)
+                and np.array_equal(nodes[:, [7, 17, 18, 19]], ref_nodes[:, [7, 17, 18, 19]]))
+        if not same and q >= FIRST_JUNCTION_NOISE_QUERY:
+            # past the noise event the two loops are different (equally valid) realisations: the planner still has to
+            # find a path in every query and stay close to the reference's amount of work
+            assert sizes[2] > 0 and sizes[3] == iters, f"query {q}: no path"
+            assert abs(cnt.sim_count - int(g["sim_steps"][q])) <= 0.5 * int(g["sim_steps"][q]), f"query {q}: sim steps {cnt.sim_count}"
+            continue
+        assert sizes[:3].tolist() == want.tolist(), f"query {q}: carried/tree/best {sizes[:3]} vs reference {want}"
+        assert sizes[3] == iters and cnt.sim_count == int(g["sim_steps"][q]), f"query {q}: sim steps"
         assert len(nodes) == len(ref_nodes)
         # discrete fields exactly (parent, goal flag, reference length, waypoint index), the rest to 1e-6 relative
         assert np.array_equal(nodes[:, [7, 17, 18, 19]], ref_nodes[:, [7, 17, 18, 19]]), f"query {q}: node bookkeeping"
         cont = [0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 11, 12, 13, 14, 15, 16]
         err = np.abs(nodes[:, cont] - ref_nodes[:, cont]) / np.maximum(1.0, np.abs(ref_nodes[:, cont]))
-        worst = max(worst, float(err.max()))
-        assert err.max() < 1e-6, f"query {q}: node values differ by {err.max()}"
-        assert abs(cost - float(g["cost"][q])) <= 1e-6 * max(1.0, abs(float(g["cost"][q])))
-        tr, rows = hp.best_traj()
-        assert rows[:len(nodes)].tolist() == g["rows"][q][:len(nodes)].tolist(), f"query {q}: trajectory lengths"
-    print(f"C5: {n_queries} consecutive queries equal to the reference (max relative deviation {worst:.2e})")
+        if q < FIRST_JUNCTION_NOISE_QUERY:
+            worst = max(worst, float(err.max()))
+            assert err.max() < 1e-6, f"query {q}: node values differ by {err.max()}"
+            assert abs(cost - float(g["cost"][q])) <= 1e-6 * max(1.0, abs(float(g["cost"][q])))
+            tr, rows = hp.best_traj()
+            assert rows[:len(nodes)].tolist() == g["rows"][q][:len(nodes)].tolist(), f"query {q}: trajectory lengths"
+            exact += 1
+    assert exact == FIRST_JUNCTION_NOISE_QUERY
+    print(f"C5: the first {exact} consecutive queries equal to the reference (max relative deviation {worst:.2e}), including the "
+          f"query whose candidate list depends on std::sort's order of equal keys; {n_queries} queries run")
+    hp.close()
+
+
+def test_single_sample_search_orders_equal_keys_like_std_sort(golden_dir):
+    """Query 41 of G5 holds an iteration whose two best parents have exactly equal keys; the reference tries them in the
+    order its std::sort leaves (the higher node id first there).  Up to that query nothing else distinguishes the tie
+    rules, so sim steps of query 41 separate them: 5128 (reference, tie mode 1) against 5135 (lower node id first)."""
+    g = np.load(os.path.join(golden_dir, "g5_replan.npz"))
+    hp = HostPlanner(samples_per_round=1, commit_path=True)
+    C.CDLL(None).srand(C.c_uint(1))
+    for q in range(42):
+        sizes, cost, cnt = hp.query(g["world"][q], g["goal"][q], g["obstacles"][q], int(g["iters"]))
+    assert cnt.sim_count == int(g["sim_steps"][41]) == 5128
     hp.close()
 
 
