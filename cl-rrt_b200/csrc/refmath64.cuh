@@ -1,0 +1,201 @@
+// refmath64.cuh — double sin / cos / tan with bit-for-bit the results of the reference platform.
+//
+// The reference integrates its vehicle model in double through the C library: sin, cos (heading) and tan (steering angle)
+// of glibc 2.39 on x86-64 (rrt/src/simulation.cpp:11-25, rrt/src/controller.cpp:56-57).  CUDA's own double routines agree
+// with glibc's to the last ulp in most calls, not in all; the states then drift apart by ~1e-13, which is harmless except
+// where the reference itself amplifies the last bit: a goal-biased reference repeats its junction point, and while the
+// controller's three-point window straddles the pair the Lagrange interpolation divides by ~1e-15 —
+// the saturated steer command takes a sign that hangs on the last bit of sin/cos/tan.  To follow the reference through
+// those steps this header restates glibc's routines operation by operation:
+//   * sin / cos: sysdeps/ieee754/dbl-64/s_sin.c (IBM Accurate Mathematical Library as simplified in glibc 2.28+): do_sin /
+//     do_cos around the 440-entry table __sincostab (x_k = k/128), TAYLOR_SIN below 0.126, reduce_sincos (Cody-Waite in
+//     four parts) up to |x| < 105414350.
+//   * tan: sysdeps/ieee754/dbl-64/s_tan.c after the removal of its slow paths (glibc 2.35+): |x| <= 1.259e-8 -> x; <= 0.0608
+//     -> odd polynomial; <= 0.787 -> table xfg (utan.tbl) + one division.  (The steering angle is saturated to +-0.52.)
+// On x86-64 CPUs with FMA, glibc's ifunc dispatch selects the build of these sources compiled with -mfma -mavx2, in which
+// the compiler contracted many a*b+c into fused multiply-adds; WHICH ones is not in the source, so the operation sequence
+// below follows the machine code of that build (Ubuntu glibc 2.39-0ubuntu8, __sin_fma / __cos_fma / __tan_fma) — every
+// fma() here is a vfmadd/vfnmadd/vfmsub there, every separate product or sum a vmulsd/vaddsd/vsubsd.  Constants are the
+// published ones (usncs.h, utan.h), the two tables are generated from the installed libm (scripts/gen_refmath64_tables.py).
+// tests/test_refmath.py compiles this header for the host (REFMATH_HOST) and compares it with the C library bit for bit
+// over the ranges the rollout uses.  Outside the restated ranges (|x| >= 105414350 for sin/cos, |x| > 0.787 for tan,
+// non-finite arguments) the functions fall back to the platform's own routine.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#ifdef REFMATH_HOST
+#define RM64_FN static inline
+#define RM64_TABLE static const
+static inline int64_t rm64_bits(double d) { int64_t u; memcpy(&u, &d, 8); return u; }
+static inline double rm64_fallback_sin(double x) { return sin(x); }
+static inline double rm64_fallback_cos(double x) { return cos(x); }
+static inline double rm64_fallback_tan(double x) { return tan(x); }
+#else
+#define RM64_FN __device__ __forceinline__
+#define RM64_TABLE static __device__ const
+__device__ __forceinline__ int64_t rm64_bits(double d) { return (int64_t)__double_as_longlong(d); }
+__device__ __noinline__ double rm64_fallback_sin(double x) { return sin(x); }
+__device__ __noinline__ double rm64_fallback_cos(double x) { return cos(x); }
+__device__ __noinline__ double rm64_fallback_tan(double x) { return tan(x); }
+#endif
+
+#include "refmath64_tables.inc"
+
+// usncs.h
+#define RM64_BIG 0x1.8p45
+#define RM64_SN3 -0x1.5555555555515p-3
+#define RM64_SN5 0x1.11110e829872fp-7
+#define RM64_CS2 0x1p-1
+#define RM64_CS4 -0x1.5555555555535p-5
+#define RM64_CS6 0x1.6c16bedd9e239p-10
+#define RM64_S1 -0x1.5555555555555p-3
+#define RM64_S2 0x1.1111111110ecep-7
+#define RM64_S3 -0x1.a01a019db08b8p-13
+#define RM64_S4 0x1.71de27b9a7ed9p-19
+#define RM64_S5 -0x1.addffc2fcdf59p-26
+#define RM64_HP0 0x1.921fb54442d18p+0
+#define RM64_HP1 0x1.1a62633145c07p-54
+#define RM64_TOINT 0x1.8p52
+#define RM64_HPINV 0x1.45f306dc9c883p-1
+#define RM64_MP1 0x1.921fb58000000p+0
+#define RM64_MP2 -0x1.dde973c000000p-27
+#define RM64_PP3 -0x1.cb3b398000000p-55
+#define RM64_PP4 -0x1.d747f23e32ed7p-83
+// utan.h
+#define RM64_G1 0x1.b096cp-27
+#define RM64_G2 0x1.f212dp-5
+#define RM64_G3 0x1.92f1ap-1
+#define RM64_D3 0x1.5555555555555p-2
+#define RM64_D5 0x1.11111111107c6p-3
+#define RM64_D7 0x1.ba1ba1cdb8745p-5
+#define RM64_D9 0x1.664ed49cfc666p-6
+#define RM64_D11 0x1.2385a3cf2e4eap-7
+#define RM64_E0 0x1.5555555554dbdp-2
+#define RM64_E1 0x1.11112e0a6b45fp-3
+
+// TAYLOR_SIN (s_sin.c): x + ((POLYNOMIAL(xx) * x - 0.5 * dx) * xx + dx)
+RM64_FN double rm64_taylor_sin(double xx, double x, double dx) {
+  double p = fma(RM64_S5, xx, RM64_S4);
+  p = fma(p, xx, RM64_S3);
+  p = fma(p, xx, RM64_S2);
+  p = fma(p, xx, RM64_S1);
+  const double h = dx * 0.5;
+  const double t = fma(xx, fma(p, x, -h), dx);
+  return x + t;
+}
+
+// do_sin (s_sin.c): sin(x + dx) for |x| < ~0.86, |dx| tiny.  `tab` = __sincostab (any address space)
+RM64_FN double rm64_do_sin(double x, double dx, const double* tab) {
+  const double xold = x;
+  if (fabs(x) < 0.126) return rm64_taylor_sin(x * x, x, dx);
+  if (x <= 0) dx = -dx;
+  const double u = RM64_BIG + fabs(x);
+  x = fabs(x) - (u - RM64_BIG);
+  const double xx = x * x;
+  const double s = x + fma(x * xx, fma(xx, RM64_SN5, RM64_SN3), dx);
+  const double c = fma(x, dx, xx * fma(xx, fma(xx, RM64_CS6, RM64_CS4), RM64_CS2));
+  const int k = (int)((uint32_t)rm64_bits(u) << 2);
+  const double sn = tab[k], ssn = tab[k + 1], cs = tab[k + 2], ccs = tab[k + 3];
+  const double cor = fma(s, cs, fma(-c, sn, fma(s, ccs, ssn)));
+  return copysign(sn + cor, xold);
+}
+
+// do_cos (s_sin.c): cos(x + dx)
+RM64_FN double rm64_do_cos(double x, double dx, const double* tab) {
+  if (x < 0) dx = -dx;
+  const double u = RM64_BIG + fabs(x);
+  x = fabs(x) - (u - RM64_BIG);
+  x = x + dx;
+  const double xx = x * x;
+  const double s = fma(x * xx, fma(xx, RM64_SN5, RM64_SN3), x);
+  const double c = xx * fma(xx, fma(xx, RM64_CS6, RM64_CS4), RM64_CS2);
+  const int k = (int)((uint32_t)rm64_bits(u) << 2);
+  const double sn = tab[k], ssn = tab[k + 1], cs = tab[k + 2], ccs = tab[k + 3];
+  const double cor = fma(-s, sn, fma(-c, cs, fma(-s, ssn, ccs)));
+  return cs + cor;
+}
+
+// reduce_sincos (s_sin.c): x = n*pi/2 + a + da, |x| < 105414350; returns n mod 4
+RM64_FN int rm64_reduce(double x, double* a, double* da) {
+  const double t = fma(x, RM64_HPINV, RM64_TOINT);
+  const double xn = t - RM64_TOINT;
+  const int n = (int)(rm64_bits(t) & 3);
+  const double y = fma(-xn, RM64_MP2, fma(-xn, RM64_MP1, x));
+  const double t2 = fma(-xn, RM64_PP3, y);
+  const double db = fma(-xn, RM64_PP3, y - t2);
+  const double b = fma(-xn, RM64_PP4, t2);
+  const double db2 = fma(-xn, RM64_PP4, t2 - b);
+  *a = b;
+  *da = db + db2;
+  return n;
+}
+
+// __sin / __cos (s_sin.c).  k = high word of |x|.  (A variant that selects the arguments first and evaluates do_sin and
+// do_cos once for both results was measured on the rollout kernel: 2 % slower than these two plain functions; so were the
+// tables in shared memory, by 6-20 %: they are read through L1 here.)
+RM64_FN double ref_sin(double x) {
+  const double* tab = rm64_sincostab;
+  const uint32_t k = (uint32_t)(rm64_bits(x) >> 32) & 0x7fffffffu;
+  if (k < 0x3e500000u) return x;                            // |x| < 2^-26
+  if (k < 0x3feb6000u) return rm64_do_sin(x, 0.0, tab);     // |x| < 0.855469
+  if (k < 0x400368fdu) {                                    // |x| < 2.426265
+    const double t = RM64_HP0 - fabs(x);
+    return copysign(rm64_do_cos(t, RM64_HP1, tab), x);
+  }
+  if (k < 0x419921FBu) {                                    // |x| < 105414350
+    double a, da;
+    const int n = rm64_reduce(x, &a, &da);
+    const double r = (n & 1) ? rm64_do_cos(a, da, tab) : rm64_do_sin(a, da, tab);
+    return (n & 2) ? -r : r;
+  }
+  return rm64_fallback_sin(x);
+}
+RM64_FN double ref_cos(double x) {
+  const double* tab = rm64_sincostab;
+  const uint32_t k = (uint32_t)(rm64_bits(x) >> 32) & 0x7fffffffu;
+  if (k < 0x3e400000u) return 1.0;                          // |x| < 2^-27
+  if (k < 0x3feb6000u) return rm64_do_cos(x, 0.0, tab);
+  if (k < 0x400368fdu) {
+    const double y = RM64_HP0 - fabs(x);
+    const double a = y + RM64_HP1;
+    const double da = (y - a) + RM64_HP1;
+    return rm64_do_sin(a, da, tab);
+  }
+  if (k < 0x419921FBu) {
+    double a, da;
+    const int n = rm64_reduce(x, &a, &da) + 1;
+    const double r = (n & 1) ? rm64_do_cos(a, da, tab) : rm64_do_sin(a, da, tab);
+    return (n & 2) ? -r : r;
+  }
+  return rm64_fallback_cos(x);
+}
+// the reference calls std::sin and std::cos on the same heading
+RM64_FN void ref_sincos(double x, double* s, double* c) { *s = ref_sin(x); *c = ref_cos(x); }
+
+// __tan (s_tan.c)
+RM64_FN double ref_tan(double x) {
+  const double* xfg = rm64_xfg;
+  const double w = fabs(x);
+  if (w <= RM64_G1) return x;
+  if (w <= RM64_G2) {
+    const double x2 = x * x;
+    double t = fma(RM64_D11, x2, RM64_D9);
+    t = fma(t, x2, RM64_D7);
+    t = fma(t, x2, RM64_D5);
+    t = fma(t, x2, RM64_D3);
+    return fma(x * x2, t, x);
+  }
+  if (w <= RM64_G3) {
+    const int i = (int)fma(256.0, w, -15.5);
+    const double z = w - xfg[4 * i];
+    const double z2 = z * z;
+    const double pz = fma(z * z2, fma(z2, RM64_E1, RM64_E0), z);
+    const double fi = xfg[4 * i + 1], gi = xfg[4 * i + 2];
+    const double t2 = ((fi + gi) * pz) / (gi - pz);
+    const double y = fi + t2;
+    return (x < 0) ? -y : y;
+  }
+  return rm64_fallback_tan(x);
+}

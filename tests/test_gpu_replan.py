@@ -57,12 +57,13 @@ class HostPlanner:
             self.h = None
 
 
-# The first query of G5 in which a goal-biased rollout crosses the duplicated junction point of its reference with the
-# 3-point window straddling the pair: the reference's Lagrange interpolation then divides
-# by ~1e-15, the saturated steer command is +-dmax with a sign that hangs on the last bit of glibc's sin/cos/tan, and the
-# device's libm differs from glibc in that bit.  The product's rollout there ends 2 steps later; every query before it is
-# bit-for-bit the reference's.
-FIRST_JUNCTION_NOISE_QUERY = 50
+# Every one of the 100 recorded queries has to equal the reference's.  Two things this loop exercises that nothing else
+# does: query 41 holds a candidate list with two exactly equal keys (std::sort's order decides which parent is tried first),
+# and in query 50 a goal-biased rollout crosses the duplicated junction point of its reference with the controller's
+# 3-point window straddling the pair — the Lagrange interpolation divides by ~1e-15 and the saturated steer command takes a
+# sign that hangs on the last bit of sin/cos/tan, which is why the kernels restate glibc's double
+# routines (csrc/refmath64.cuh).  With CUDA's own libm that rollout ends two steps later and the loops part ways there.
+FIRST_JUNCTION_NOISE_QUERY = 100  # = no query is exempt
 
 
 def test_receding_horizon_loop_matches_reference(golden_dir):
