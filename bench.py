@@ -287,7 +287,7 @@ def run_ours(args):
         every rank appends all ranks' chunks in rank order (= global sample order), so the trees stay identical."""
         ptr, n = pl.round_records()
         src = _as_cuda_tensor(ptr, max_rec * rec_bytes, local)
-        out, counts, stride = gather_records(src, n, world, counts_t, gathered)
+        out, counts, stride = gather_records(src, n, world, counts_t, gathered, sync=False)  # planner and torch share `stream`
         if stride == 0:
             return 0
         pl.append_records(out.data_ptr(), counts, stride)

@@ -27,6 +27,7 @@
 
 #ifdef REFMATH_HOST
 #define RM64_FN static inline
+#define RM64_CORE static inline
 #define RM64_TABLE static const
 static inline int64_t rm64_bits(double d) { int64_t u; memcpy(&u, &d, 8); return u; }
 static inline double rm64_fallback_sin(double x) { return sin(x); }
@@ -34,6 +35,11 @@ static inline double rm64_fallback_cos(double x) { return cos(x); }
 static inline double rm64_fallback_tan(double x) { return tan(x); }
 #else
 #define RM64_FN __device__ __forceinline__
+#ifdef RM64_NOINLINE_CORE
+#define RM64_CORE __device__ __noinline__
+#else
+#define RM64_CORE __device__ __forceinline__
+#endif
 #define RM64_TABLE static __device__ const
 __device__ __forceinline__ int64_t rm64_bits(double d) { return (int64_t)__double_as_longlong(d); }
 __device__ __noinline__ double rm64_fallback_sin(double x) { return sin(x); }
@@ -87,7 +93,7 @@ RM64_FN double rm64_taylor_sin(double xx, double x, double dx) {
 }
 
 // do_sin (s_sin.c): sin(x + dx) for |x| < ~0.86, |dx| tiny.  `tab` = __sincostab (any address space)
-RM64_FN double rm64_do_sin(double x, double dx, const double* tab) {
+RM64_CORE double rm64_do_sin(double x, double dx, const double* tab) {
   const double xold = x;
   if (fabs(x) < 0.126) return rm64_taylor_sin(x * x, x, dx);
   if (x <= 0) dx = -dx;
@@ -103,7 +109,7 @@ RM64_FN double rm64_do_sin(double x, double dx, const double* tab) {
 }
 
 // do_cos (s_sin.c): cos(x + dx)
-RM64_FN double rm64_do_cos(double x, double dx, const double* tab) {
+RM64_CORE double rm64_do_cos(double x, double dx, const double* tab) {
   if (x < 0) dx = -dx;
   const double u = RM64_BIG + fabs(x);
   x = fabs(x) - (u - RM64_BIG);

@@ -19,10 +19,13 @@ def shard_range(n_total, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_records(local, n_local, world, counts_buf=None, gather_buf=None):
+def gather_records(local, n_local, world, counts_buf=None, gather_buf=None, sync=True):
     """local: uint8 tensor holding at least n_local*RECORD_BYTES bytes (this rank's records, packed).
     Returns (gathered, counts, stride): `gathered` is a uint8 tensor of world*stride*RECORD_BYTES bytes in which rank
-    r's records start at r*stride*RECORD_BYTES; counts[r] = number of records of rank r (numpy int32)."""
+    r's records start at r*stride*RECORD_BYTES; counts[r] = number of records of rank r (numpy int32).
+    A NCCL collective is only ordered with torch's CURRENT stream: with sync=True (default) the host waits for it, so that
+    the gathered buffer may be consumed on any stream (clrrt_append_records runs on the planner's own stream unless the
+    planner was created on torch's); sync=False is for callers whose planner shares torch's current stream (bench.py)."""
     dev = local.device
     mine = torch.tensor([n_local], dtype=torch.int32, device=dev)
     counts_t = counts_buf if counts_buf is not None else torch.zeros(world, dtype=torch.int32, device=dev)
@@ -38,6 +41,8 @@ def gather_records(local, n_local, world, counts_buf=None, gather_buf=None):
         local = padded
     out = gather_buf[:world * nbytes] if gather_buf is not None else torch.empty(world * nbytes, dtype=torch.uint8, device=dev)
     dist.all_gather_into_tensor(out, local[:nbytes].contiguous())
+    if sync and out.is_cuda:
+        torch.cuda.current_stream(dev).synchronize()
     return out, counts, stride
 
 
