@@ -63,7 +63,7 @@ struct clrrt_ctx {
   // candidate search: nodes and samples sorted along the goal bearing (nearest.cuh)
   void* nn_mem = nullptr;
   NNSortArgs nn{};
-  float *d_tile_ulo = nullptr, *d_tile_uhi = nullptr, *d_tile_ce = nullptr;
+  float *d_tile_ulo = nullptr, *d_tile_uhi = nullptr, *d_tile_vlo = nullptr, *d_tile_vhi = nullptr, *d_tile_ce = nullptr;
   NodeRecord* d_export = nullptr;    // staging of clrrt_tree_download_range
   size_t export_cap = 0;
   void* d_init = nullptr;            // prepared rollouts of a round (setup_kernel) + per-thread scratch records
@@ -80,6 +80,7 @@ struct clrrt_ctx {
   unsigned long long* d_counters = nullptr;  // 8
   // K = 1: the reference's order of equal keys (nearest_reference_ties)
   float* d_all_key = nullptr; uint8_t* d_all_feas = nullptr;
+  int nn_lateral_log2 = -1;  // >= 0: fixed number of lateral bins of the spatial order (tests); -1: by tree size
   int tie_mode = 1;          // 1: std::sort's order of equal keys for single-sample searches; 0: lower node id everywhere
   long long tie_sorts = 0;   // searches that had to repeat the reference's sort on the host
   unsigned long long* d_timeline = nullptr;  // CLRRT_PHASE_CLOCKS builds: 3 words per staging slot (rollout.cuh)
@@ -299,7 +300,7 @@ int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_r
   ok &= mal((void**)&ctx->d_bucket, K * CLRRT_SORT_LIMIT);
   {
     const size_t n8 = ((size_t)tree_capacity + 7) & ~(size_t)7, k8 = (K + 7) & ~(size_t)7;
-    const size_t bytes = n8 * (7 * 8 + 3 * 4 + 4 + 4) + (n8 + k8) * 4 + k8 * 4 + 3 * NN_BINS * 4 + 3 * (n8 / NEAREST_TILE + 8) * 4 + 1024;
+    const size_t bytes = n8 * (7 * 8 + 3 * 4 + 4 + 4) + (n8 + k8) * 4 + k8 * 4 + 3 * NN_BINS * 4 + 5 * (n8 / NEAREST_TILE + 8) * 4 + 1024;
     ok &= mal(&ctx->nn_mem, bytes);
     if (ok) {
       unsigned char* p = reinterpret_cast<unsigned char*>(ctx->nn_mem);
@@ -317,6 +318,8 @@ int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_r
       ctx->d_tile_ce = reinterpret_cast<float*>(take((n8 / NEAREST_TILE + 8) * 4));
       ctx->d_tile_ulo = reinterpret_cast<float*>(take((n8 / NEAREST_TILE + 8) * 4));
       ctx->d_tile_uhi = reinterpret_cast<float*>(take((n8 / NEAREST_TILE + 8) * 4));
+      ctx->d_tile_vlo = reinterpret_cast<float*>(take((n8 / NEAREST_TILE + 8) * 4));
+      ctx->d_tile_vhi = reinterpret_cast<float*>(take((n8 / NEAREST_TILE + 8) * 4));
     }
   }
   ctx->init_stride = ((K * CLRRT_SORT_LIMIT + (size_t)ctx->num_sms * 4 * ROLLOUT_THREADS) + 31) & ~(size_t)31;
@@ -727,14 +730,21 @@ static int nearest_dev(clrrt_ctx* ctx, const double* d_samples, const uint8_t* d
   s.tree = ctx->tree; s.n_nodes = ctx->n_tree; s.K = K; s.sample_xy = d_samples; s.heuristic = d_heur;
   s.cb = (float)std::cos(beta); s.sb = (float)std::sin(beta);
   s.u0 = -15.0f;
-  const float bin_w = (float)((dgoal + 40.0) / NN_BINS);
+  // large trees: the bins become (axis slab, lateral bin) pairs, so that tiles are compact in both directions and a
+  // block can skip the tiles of a slab that lie to the side of its samples (lateral range: the +-7 m sampling band)
+  s.nl_log2 = ctx->nn_lateral_log2 >= 0 ? ctx->nn_lateral_log2 : (ctx->n_tree >= 98304 ? 4 : ctx->n_tree >= 24576 ? 2 : 0);
+  const float bin_w = (float)((dgoal + 40.0) / (NN_BINS >> s.nl_log2));
   s.inv_bin = 1.0f / bin_w;
+  s.v0 = -8.0f;
+  const float vbin_w = 16.0f / (float)(1 << s.nl_log2);
+  s.inv_vbin = 1.0f / vbin_w;
   const int n_el = ctx->n_tree + K, n_tiles = (ctx->n_tree + NEAREST_TILE - 1) / NEAREST_TILE;
   CK(cudaMemsetAsync(s.hist, 0, 3 * NN_BINS * sizeof(int32_t), st));
   nn_bin_kernel<<<(n_el + 255) / 256, 256, 0, st>>>(s);
   nn_scan_kernel<<<2, NN_BINS, 0, st>>>(s.hist);
   nn_scatter_kernel<<<(n_el + 255) / 256, 256, 0, st>>>(s);
-  nn_tile_kernel<<<n_tiles, NEAREST_TILE, 0, st>>>(s.sbin, s.ce, ctx->n_tree, s.u0, bin_w, ctx->d_tile_ulo, ctx->d_tile_uhi, ctx->d_tile_ce);
+  nn_tile_kernel<<<n_tiles, NEAREST_TILE, 0, st>>>(s.sbin, s.ce, ctx->n_tree, s.u0, bin_w, s.v0, vbin_w, s.nl_log2, ctx->d_tile_ulo,
+                                                   ctx->d_tile_uhi, ctx->d_tile_vlo, ctx->d_tile_vhi, ctx->d_tile_ce);
   CK(cudaGetLastError());
   // 2. the search
   NearestArgs a;
@@ -742,7 +752,7 @@ static int nearest_dev(clrrt_ctx* ctx, const double* d_samples, const uint8_t* d
   a.cand = d_cand; a.key = d_key; a.count = d_count; a.feas_len = ctx->dprm.feas_len;
   a.so.n_nodes = ctx->n_tree; a.so.n_tiles = n_tiles; a.so.node_id = s.node_id;
   a.so.nx = s.nx; a.so.ny = s.ny; a.so.rbx = s.rbx; a.so.rby = s.rby; a.so.dpx = s.dpx; a.so.dpy = s.dpy; a.so.ang = s.ang;
-  a.so.ca = s.ca; a.so.sa = s.sa; a.so.ce = s.ce; a.so.tile_ulo = ctx->d_tile_ulo; a.so.tile_uhi = ctx->d_tile_uhi; a.so.tile_ce = ctx->d_tile_ce;
+  a.so.ca = s.ca; a.so.sa = s.sa; a.so.ce = s.ce; a.so.tile_ulo = ctx->d_tile_ulo; a.so.tile_uhi = ctx->d_tile_uhi; a.so.tile_vlo = ctx->d_tile_vlo; a.so.tile_vhi = ctx->d_tile_vhi; a.so.tile_ce = ctx->d_tile_ce;
   a.so.sample_id = s.sample_id; a.so.cb = s.cb; a.so.sb = s.sb;
   const int blocks = (K + NEAREST_WARPS - 1) / NEAREST_WARPS;
   nearest_sorted_kernel<<<blocks, NEAREST_THREADS, 0, ctx->stream>>>(a);
@@ -986,7 +996,10 @@ int clrrt_set_tie_mode(clrrt_ctx* ctx, int mode) {
 long long clrrt_tie_sorts(const clrrt_ctx* ctx) { return ctx ? ctx->tie_sorts : -1; }
 
 int clrrt_set_nearest_mode(clrrt_ctx* ctx, int mode) {
+  // 0 auto, 1 spatial order always, 2 never; 16 + L: spatial order always with 2^L lateral bins (L = 0..5), for tests
+  if (ctx && mode >= 16 && mode <= 21) { ctx->nn_mode = 1; ctx->nn_lateral_log2 = mode - 16; return CLRRT_OK; }
   if (!ctx || mode < 0 || mode > 2) return CLRRT_ERR_ARG;
+  ctx->nn_lateral_log2 = -1;
   ctx->nn_mode = mode;
   return CLRRT_OK;
 }

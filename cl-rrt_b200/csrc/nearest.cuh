@@ -36,6 +36,8 @@ struct NearestSorted {
   const float *ca, *sa, *ce;
   const float* tile_ulo;    // [n_tiles] axis interval of every tile of NEAREST_TILE sorted nodes
   const float* tile_uhi;
+  const float* tile_vlo;    // [n_tiles] lateral interval (infinite for tiles that span more than one axis slab)
+  const float* tile_vhi;
   const float* tile_ce;     // [n_tiles] smallest costE in the tile (bound for the optimise key costE + Dubins)
   const int32_t* sample_id; // [K] original index of the sample at a sorted position
   float cb, sb;             // axis direction
@@ -59,7 +61,9 @@ struct NNSortArgs {
   int32_t n_nodes, K;
   const double* sample_xy;
   const uint8_t* heuristic;
-  float cb, sb, u0, inv_bin;
+  float cb, sb, u0, inv_bin;   // axis: slab = (u - u0) * inv_bin, NN_BINS >> nl_log2 slabs
+  float v0, inv_vbin;          // lateral coordinate v = -x sb + y cb: 1 << nl_log2 bins from v0
+  int32_t nl_log2;             // bin = slab << nl_log2 | lateral bin (0: axis only)
   int32_t* bin;        // [n_nodes + K] bin of every element (nodes first)
   int32_t* hist;       // [3 * NN_BINS]: nodes; samples with the explore key; samples with the optimise key (so that the 8
                        // samples of a block share a heuristic: the two keys prune very differently)
@@ -71,19 +75,20 @@ struct NNSortArgs {
   int32_t* sample_id;
 };
 
-__device__ __forceinline__ int nn_bin_of(float u, float u0, float inv_bin) {
+__device__ __forceinline__ int nn_bin_of(float u, float u0, float inv_bin, int nbins) {
   const float b = (u - u0) * inv_bin;
-  return b >= 0.0f ? min((int)b, NN_BINS - 1) : 0;  // NaN and out-of-range elements land in the end bins
+  return b >= 0.0f ? min((int)b, nbins - 1) : 0;  // NaN and out-of-range elements land in the end bins
 }
 
 __global__ void __launch_bounds__(256) nn_bin_kernel(const NNSortArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int key = -1;
   if (i < a.n_nodes + a.K) {
-    float u;
-    if (i < a.n_nodes) u = (float)a.tree.x[i] * a.cb + (float)a.tree.y[i] * a.sb;
-    else u = (float)a.sample_xy[2 * (i - a.n_nodes)] * a.cb + (float)a.sample_xy[2 * (i - a.n_nodes) + 1] * a.sb;
-    int b = nn_bin_of(u, a.u0, a.inv_bin);
+    float x, y;
+    if (i < a.n_nodes) { x = (float)a.tree.x[i]; y = (float)a.tree.y[i]; }
+    else { x = (float)a.sample_xy[2 * (i - a.n_nodes)]; y = (float)a.sample_xy[2 * (i - a.n_nodes) + 1]; }
+    const float u = x * a.cb + y * a.sb, v = y * a.cb - x * a.sb;
+    int b = (nn_bin_of(u, a.u0, a.inv_bin, NN_BINS >> a.nl_log2) << a.nl_log2) | nn_bin_of(v, a.v0, a.inv_vbin, 1 << a.nl_log2);
     if (i >= a.n_nodes && a.heuristic[i - a.n_nodes]) b += NN_BINS;
     a.bin[i] = b;
     key = (i < a.n_nodes ? 0 : NN_BINS) + b;
@@ -141,8 +146,10 @@ __global__ void __launch_bounds__(256) nn_scatter_kernel(const NNSortArgs a) {
 // range, so their outer edges are infinite; 1 cm of slack covers the float rounding of the bin assignment), and the
 // smallest costE (NaN-safe: a tile with a NaN cost reports -inf and is never skipped).
 __global__ void __launch_bounds__(NEAREST_TILE) nn_tile_kernel(const int32_t* __restrict__ sbin, const float* __restrict__ ce,
-                                                                int n_nodes, float u0, float bin_w, float* __restrict__ ulo,
-                                                                float* __restrict__ uhi, float* __restrict__ cemin) {
+                                                                int n_nodes, float u0, float bin_w, float v0, float vbin_w,
+                                                                int nl_log2, float* __restrict__ ulo, float* __restrict__ uhi,
+                                                                float* __restrict__ vlo, float* __restrict__ vhi,
+                                                                float* __restrict__ cemin) {
   __shared__ float smn[NEAREST_TILE / 32];
   const int t = blockIdx.x, i = t * NEAREST_TILE + threadIdx.x;
   float mn = INFINITY;
@@ -153,8 +160,14 @@ __global__ void __launch_bounds__(NEAREST_TILE) nn_tile_kernel(const int32_t* __
   if (threadIdx.x == 0) {
     for (int w = 1; w < NEAREST_TILE / 32; w++) mn = fminf(mn, smn[w]);
     const int b0 = sbin[t * NEAREST_TILE], b1 = sbin[min(t * NEAREST_TILE + NEAREST_TILE - 1, n_nodes - 1)];
-    ulo[t] = b0 <= 0 ? -INFINITY : u0 + (float)b0 * bin_w - 0.01f;
-    uhi[t] = b1 >= NN_BINS - 1 ? INFINITY : u0 + (float)(b1 + 1) * bin_w + 0.01f;
+    const int ns = NN_BINS >> nl_log2, nl = 1 << nl_log2;
+    const int s0 = b0 >> nl_log2, s1 = b1 >> nl_log2, l0 = b0 & (nl - 1), l1 = b1 & (nl - 1);
+    ulo[t] = s0 <= 0 ? -INFINITY : u0 + (float)s0 * bin_w - 0.01f;
+    uhi[t] = s1 >= ns - 1 ? INFINITY : u0 + (float)(s1 + 1) * bin_w + 0.01f;
+    // within one slab the nodes are ordered by lateral bin; a tile that spans several slabs covers every lateral position
+    const bool one = s0 == s1 && nl > 1;
+    vlo[t] = (!one || l0 <= 0) ? -INFINITY : v0 + (float)l0 * vbin_w - 0.01f;
+    vhi[t] = (!one || l1 >= nl - 1) ? INFINITY : v0 + (float)(l1 + 1) * vbin_w + 0.01f;
     cemin[t] = mn;
   }
 }
@@ -234,11 +247,12 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
   const bool live = js < a.K;
   const int j = live ? so.sample_id[js] : 0;
   double sx = 0, sy = 0;
-  float su = 0.0f;
+  float su = 0.0f, sv = 0.0f;
   bool optimize = false;
   if (live) {
     sx = a.sample_xy[2 * j]; sy = a.sample_xy[2 * j + 1]; optimize = a.heuristic[j] != 0;
     su = (float)sx * so.cb + (float)sy * so.sb;
+    sv = (float)sy * so.cb - (float)sx * so.sb;
   }
   float lk = INFINITY;  // entry `lane` of the list (lanes >= 10 stay at +inf / INT_MAX and never take part)
   int lid = INT_MAX;
@@ -268,17 +282,24 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
     if (t >= so.n_tiles) { open_up = false; continue; }
     // does any sample of the block still need this tile?  axis distance <= Euclidean distance <= key / 0.999 (+ the
     // tile's smallest costE for the optimise key)
-    bool want = false;
+    bool want = false, axis_open = false;
     if (live) {
       const float du = fmaxf(fmaxf(so.tile_ulo[t] - su, su - so.tile_uhi[t]), 0.0f);
-      want = !(0.999f * du + (optimize ? so.tile_ce[t] : 0.0f) > T);
+      const float dv = fmaxf(fmaxf(so.tile_vlo[t] - sv, sv - so.tile_vhi[t]), 0.0f);
+      // (dv == 0 for tiles without a lateral interval)
+      want = !(0.999f * sqrtf(du * du + dv * dv) + (optimize ? so.tile_ce[t] : 0.0f) > T);
+      axis_open = !(0.999f * du > T);
     }
     if (!__syncthreads_or(want ? 1 : 0)) {
-      // nobody needs this tile: every tile farther out in the same direction is farther from every sample (the
-      // intervals are monotone along the tile order) and T only shrinks, so the direction is finished
-      if (step == 0) { open_up = false; open_dn = false; }  // (cannot happen while a list is still open: T is infinite)
-      else if (up) open_up = false;
-      else open_dn = false;
+      // Nobody needs this tile: it is skipped.  The DIRECTION is finished only when the axis distance alone rules the tile
+      // out for every sample: the axis intervals are monotone along the tile order and T only shrinks, so every tile
+      // farther out is ruled out too.  (The lateral interval and the tile's smallest costE are not monotone along the
+      // order — the root, 30 m behind a sample, is the best parent by the optimise key — so they only skip.)
+      if (!__syncthreads_or(axis_open ? 1 : 0)) {
+        if (step == 0) { open_up = false; open_dn = false; }  // (cannot happen while a list is still open: T is infinite)
+        else if (up) open_up = false;
+        else open_dn = false;
+      }
       continue;
     }
     const int base = t * NEAREST_TILE;

@@ -206,7 +206,8 @@ long long clrrt_tie_sorts(const clrrt_ctx* ctx);
  * grid path only.  Results do not depend on it. */
 int clrrt_set_grid_cell(clrrt_ctx* ctx, double metres);
 /* Candidate search: 0 = pick by problem size (default), 1 = always sort nodes and samples along the goal bearing first,
- * 2 = never.  Results do not depend on it. */
+ * 2 = never; 16 + L (L = 0..5): always sort, into (axis slab, lateral bin) cells with 2^L lateral bins — the order trees
+ * of more than ~25 000 nodes get by default (L = 2, from ~100 000 nodes L = 4).  Results do not depend on it. */
 int clrrt_set_nearest_mode(clrrt_ctx* ctx, int mode);
 
 #ifdef __cplusplus

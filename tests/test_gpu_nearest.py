@@ -21,7 +21,9 @@ def ulp_diff(a, b):
     return np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64))
 
 
-@pytest.mark.parametrize("mode", [2, 1])  # storage-order search / nodes and samples sorted along the goal bearing first
+# storage-order search / nodes and samples sorted along the goal bearing first / sorted into (axis slab, lateral bin) cells
+# with 4 and 16 lateral bins (the order large trees get; forced here on small ones)
+@pytest.mark.parametrize("mode", [2, 1, 18, 20])
 @pytest.mark.parametrize("N", [1, 64, 250, 1500])
 def test_g2_candidate_lists(clrrt, planner, golden_dir, N, mode):
     g = np.load(os.path.join(golden_dir, "g2_nearest.npz"))
@@ -68,7 +70,7 @@ def test_large_snapshot_vs_oracle(clrrt, planner):
     tree = planner.tree_download_records()
     orc.tree_import(tree)
     oc, ok, on = orc.nearest_batch(s, h)
-    for mode in (2, 1, 0):
+    for mode in (2, 1, 0, 17, 18, 20, 21):
         planner.set_nearest_mode(mode)
         cand, key, cnt = planner.nearest_batch(s, h)
         assert np.array_equal(cnt, on)
@@ -81,7 +83,7 @@ def test_large_snapshot_vs_oracle(clrrt, planner):
     orc.tree_init(car, goal2, 5.0)
     orc.tree_import(tree)
     oc, ok, on = orc.nearest_batch(s, h)
-    for mode in (2, 1):
+    for mode in (2, 1, 18, 20):
         planner.set_nearest_mode(mode)
         cand, key, cnt = planner.nearest_batch(s, h)
         assert np.array_equal(cnt, on) and np.array_equal(key, ok) and np.array_equal(cand, oc)
