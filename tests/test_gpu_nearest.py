@@ -88,3 +88,32 @@ def test_large_snapshot_vs_oracle(clrrt, planner):
         cand, key, cnt = planner.nearest_batch(s, h)
         assert np.array_equal(cnt, on) and np.array_equal(key, ok) and np.array_equal(cand, oc)
     planner.set_nearest_mode(0)
+
+
+def test_spatial_orders_agree_on_a_large_tree(clrrt, golden_dir):
+    """A tree of ~10^5 nodes (the 200 ms query of config C1): the storage-order search (every tile, every node) against the
+    sorted searches with 1, 4 and 16 lateral bins and the default.  With the optimise key the best parents of many samples
+    are the root and its copies, tens of metres behind the sample: a search that closes a direction on anything but the
+    axis distance loses them."""
+    import bench
+    K = 16384
+    pl = clrrt.Planner(device=0, tree_capacity=(1 << 18), max_round=K)
+    try:
+        pl.set_query(bench.C1_CAR, bench.C1_GOAL, bench.VMAX)
+        pl.set_obstacles(bench.scene_c1_boxes())
+        pl.tree_reset(clrrt.root_node(bench.C1_CAR))
+        clrrt.draw_samples(bench.C1_GOAL, 1, seed=1)
+        while pl.tree_size() < 100000:
+            s, h = clrrt.draw_samples(bench.C1_GOAL, K)
+            pl.expand_round(s, h)
+        s, h = clrrt.draw_samples(bench.C1_GOAL, 4096)
+        assert h.any() and not h.all()
+        pl.set_nearest_mode(2)
+        want = pl.nearest_batch(s, h)
+        for mode in (16, 18, 20, 0):
+            pl.set_nearest_mode(mode)
+            got = pl.nearest_batch(s, h)
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b), f"mode {mode}"
+    finally:
+        pl.close()
