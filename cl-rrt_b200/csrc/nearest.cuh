@@ -224,6 +224,16 @@ __device__ __forceinline__ bool feasible_node(double sx, double sy, double rbx, 
   return !(sqrt(l2) < feas_len);
 }
 
+// Stage 1 of both searches: can the node enter the list at all?  key >= 0.999 d (+ costE), so a node with
+// 0.999 d + costE > T is out.  Evaluated on float copies of the positions, squared (no square root, no double arithmetic:
+// this test runs for every node of every visited tile): d > (T - costE) / 0.999 + slack, with `slack` = 1 mm + the float
+// rounding of the two positions, and one part in 10^6 for the rounding of the squares.  NaNs are kept.
+__device__ __forceinline__ bool stage1_keep(float ex, float ey, float ce, float T, float slack) {
+  const float R = (T - ce) * (1.0f / 0.999f) + slack;
+  const float d2 = __fmaf_rn(ex, ex, ey * ey);
+  return !(R < 0.0f) && !(d2 * 0.999999f > R * R);
+}
+
 // The running top-10 of a sample lives in registers of lanes 0..9 of its warp (lane r = r-th best so far), ordered by
 // (key, node id).  Its last entry T bounds the search: the Dubins key is never below the Euclidean distance from
 // the node to the sample (checked over the whole float domain of dubinsDistance: key >= (1 - 3e-6) d outside the turning
@@ -236,6 +246,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
   __shared__ double s_nx[NEAREST_TILE], s_ny[NEAREST_TILE], s_rbx[NEAREST_TILE], s_rby[NEAREST_TILE];
   __shared__ double s_dpx[NEAREST_TILE], s_dpy[NEAREST_TILE], s_ang[NEAREST_TILE];
   __shared__ float s_ca[NEAREST_TILE], s_sa[NEAREST_TILE], s_ce[NEAREST_TILE];
+  __shared__ float s_fx[NEAREST_TILE], s_fy[NEAREST_TILE];  // node positions rounded to float: stage 1 only
   __shared__ int32_t s_id[NEAREST_TILE];
   __shared__ uint16_t s_idx[NEAREST_WARPS][NEAREST_TILE];
   __shared__ uint16_t s_idx2[NEAREST_WARPS][NEAREST_TILE];
@@ -254,6 +265,8 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
     su = (float)sx * so.cb + (float)sy * so.sb;
     sv = (float)sy * so.cb - (float)sx * so.sb;
   }
+  const float fsx = (float)sx, fsy = (float)sy;
+  const float slack = 1.0e-3f + 4.0e-7f * (fabsf(fsx) + fabsf(fsy));
   float lk = INFINITY;  // entry `lane` of the list (lanes >= 10 stay at +inf / INT_MAX and never take part)
   int lid = INT_MAX;
   float T = INFINITY;   // key and id of the 10th entry (warp-uniform)
@@ -306,7 +319,8 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
     const int n = min(NEAREST_TILE, so.n_nodes - base);
     if ((int)threadIdx.x < n) {
       const int g = base + threadIdx.x;
-      s_nx[threadIdx.x] = so.nx[g]; s_ny[threadIdx.x] = so.ny[g];
+      const double nxg = so.nx[g], nyg = so.ny[g];
+      s_nx[threadIdx.x] = nxg; s_ny[threadIdx.x] = nyg; s_fx[threadIdx.x] = (float)nxg; s_fy[threadIdx.x] = (float)nyg;
       s_rbx[threadIdx.x] = so.rbx[g]; s_rby[threadIdx.x] = so.rby[g];
       s_dpx[threadIdx.x] = so.dpx[g]; s_dpy[threadIdx.x] = so.dpy[g];
       s_ang[threadIdx.x] = so.ang[g];
@@ -320,11 +334,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
       for (int i0 = 0; i0 < n; i0 += 32) {
         const int i = i0 + lane;
         bool keep = false;
-        if (i < n) {
-          const float ex = (float)(sx - s_nx[i]), ey = (float)(sy - s_ny[i]);
-          const float lb = 0.999f * sqrtf(ex * ex + ey * ey) + (optimize ? s_ce[i] : 0.0f);
-          keep = !(lb > T);  // NaN bounds are kept
-        }
+        if (i < n) keep = stage1_keep(fsx - s_fx[i], fsy - s_fy[i], optimize ? s_ce[i] : 0.0f, T, slack);
         const unsigned m = __ballot_sync(FULL_MASK, keep);
         if (keep) s_idx[warp][c1 + __popc(m & lt)] = (uint16_t)i;
         c1 += __popc(m);
@@ -402,6 +412,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_topk_kernel(const Nea
   __shared__ double s_nx[NEAREST_TILE], s_ny[NEAREST_TILE], s_rbx[NEAREST_TILE], s_rby[NEAREST_TILE];
   __shared__ double s_dpx[NEAREST_TILE], s_dpy[NEAREST_TILE], s_ang[NEAREST_TILE];
   __shared__ float s_ca[NEAREST_TILE], s_sa[NEAREST_TILE], s_ce[NEAREST_TILE];
+  __shared__ float s_fx[NEAREST_TILE], s_fy[NEAREST_TILE];  // node positions rounded to float: stage 1 only
   __shared__ uint16_t s_idx[NEAREST_WARPS][NEAREST_TILE];
   __shared__ uint16_t s_idx2[NEAREST_WARPS][NEAREST_TILE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -411,6 +422,8 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_topk_kernel(const Nea
   double sx = 0, sy = 0;
   bool optimize = false;
   if (live) { sx = a.sample_xy[2 * j]; sy = a.sample_xy[2 * j + 1]; optimize = a.heuristic[j] != 0; }
+  const float fsx = (float)sx, fsy = (float)sy;
+  const float slack = 1.0e-3f + 4.0e-7f * (fabsf(fsx) + fabsf(fsy));
   float lk = INFINITY;  // entry `lane` of the list (lanes >= 10 stay at +inf / INT_MAX and never take part)
   int lid = INT_MAX;
   float T = INFINITY;   // key and id of the 10th entry (warp-uniform)
@@ -421,7 +434,8 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_topk_kernel(const Nea
     __syncthreads();
     if ((int)threadIdx.x < n) {
       const int g = base + threadIdx.x;
-      s_nx[threadIdx.x] = a.tree.x[g]; s_ny[threadIdx.x] = a.tree.y[g];
+      const double nxg = a.tree.x[g], nyg = a.tree.y[g];
+      s_nx[threadIdx.x] = nxg; s_ny[threadIdx.x] = nyg; s_fx[threadIdx.x] = (float)nxg; s_fy[threadIdx.x] = (float)nyg;
       const double rbx = a.tree.rbx[g], rby = a.tree.rby[g];
       s_rbx[threadIdx.x] = rbx; s_rby[threadIdx.x] = rby;
       s_dpx[threadIdx.x] = rbx - a.tree.rfx[g]; s_dpy[threadIdx.x] = rby - a.tree.rfy[g];
@@ -435,11 +449,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_topk_kernel(const Nea
       for (int i0 = 0; i0 < n; i0 += 32) {
         const int i = i0 + lane;
         bool keep = false;
-        if (i < n) {
-          const float ex = (float)(sx - s_nx[i]), ey = (float)(sy - s_ny[i]);
-          const float lb = 0.999f * sqrtf(ex * ex + ey * ey) + (optimize ? s_ce[i] : 0.0f);
-          keep = !(lb > T);  // NaN bounds are kept
-        }
+        if (i < n) keep = stage1_keep(fsx - s_fx[i], fsy - s_fy[i], optimize ? s_ce[i] : 0.0f, T, slack);
         const unsigned m = __ballot_sync(FULL_MASK, keep);
         if (keep) s_idx[warp][c1 + __popc(m & lt)] = (uint16_t)i;
         c1 += __popc(m);
