@@ -8,7 +8,7 @@ pl = clrrt.Planner(device=0, tree_capacity=bench.TREE_SNAPSHOT + 2 * bench.K_ROU
 boxes, smp, heu = bench.build_workload(pl, clrrt, 0, 1)
 n0 = pl.tree_size()
 for bps in (0, 2, 1):
-    for rf in (4, 8, 12, 16, 24):
+    for rf in (1, 2, 4, 8):
         pl.set_tuning(refill_min=rf, blocks_per_sm=bps)
         best = 1e9
         for r in range(3):
