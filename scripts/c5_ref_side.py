@@ -5,6 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from cpulib import CpuPlanner
+os.makedirs(os.path.join(ROOT, "variants"), exist_ok=True)
 g = np.load(os.path.join(ROOT, "tests/golden/g5_replan.npz"))
 Q = int(sys.argv[1]) if len(sys.argv) > 1 else 41
 out = []
