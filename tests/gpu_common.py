@@ -6,7 +6,7 @@ import pytest
 
 DISC = [7, 12, 13, 14, 15, 16, 20, 21, 22]   # IDwp, endReached, goalReached, n_steps, fail, n_ref, tainted, trace, idwp0
 CONT = [0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 11, 17, 18, 19]
-REL_TOL = 1e-6  # north-star: states and costs within 1e-6 relative (measured: ~1e-13)
+REL_TOL = 1e-6  # north-star: states and costs within 1e-6 relative; measured: 0 (the kernels evaluate glibc's libm)
 
 
 def have_gpu():
@@ -21,11 +21,15 @@ def rel_err(got, want):
     return np.abs(got - want) / np.maximum(1.0, np.abs(want))
 
 
-def assert_rollouts_match(got, want, what=""):
+def assert_rollouts_match(got, want, what="", exact=True):
+    """Discrete outputs exactly; states and costs bit-equal (exact=True: everything but the exp() of the exact-distance
+    cost runs through restated glibc routines or IEEE-exact operations) or within REL_TOL."""
     d = got[:, DISC] != want[:, DISC]
     assert not d.any(), f"{what}: discrete outputs differ in rows {np.where(d.any(1))[0][:10]}"
     e = rel_err(got[:, CONT], want[:, CONT])
     assert np.nanmax(e) < REL_TOL, f"{what}: max relative error {np.nanmax(e)}"
+    if exact:
+        assert np.nanmax(e) == 0.0, f"{what}: states/costs not bit-equal, max relative error {np.nanmax(e)}"
     return float(np.nanmax(e))
 
 
