@@ -205,3 +205,66 @@ RM64_FN double ref_tan(double x) {
   }
   return rm64_fallback_tan(x);
 }
+
+// __exp (sysdeps/ieee754/dbl-64/e_exp.c: the ARM Optimized Routines exp glibc adopted in 2.28, N = 128, degree-5 polynomial),
+// again in the operation order of the FMA build.  Used by the exact-distance cost W2 * exp(-W3 * Dobs) (simulation.cpp:91).
+#define RM64_EXP_INVLN2N 0x1.71547652b82fep+7
+#define RM64_EXP_SHIFT 0x1.8p52
+#define RM64_EXP_NEGLN2HIN -0x1.62e42fefa0000p-8
+#define RM64_EXP_NEGLN2LON -0x1.cf79abc9e3b3ap-47
+#define RM64_EXP_C2 0x1.ffffffffffdbdp-2
+#define RM64_EXP_C3 0x1.555555555543cp-3
+#define RM64_EXP_C4 0x1.55555cf172b91p-5
+#define RM64_EXP_C5 0x1.1111167a4d017p-7
+#ifdef REFMATH_HOST
+static inline double rm64_from_bits(uint64_t u) { double d; memcpy(&d, &u, 8); return d; }
+static inline double rm64_fallback_exp(double x) { return exp(x); }
+#else
+__device__ __forceinline__ double rm64_from_bits(uint64_t u) { return __longlong_as_double((long long)u); }
+__device__ __noinline__ double rm64_fallback_exp(double x) { return exp(x); }
+#endif
+RM64_FN double ref_exp(double x) {
+  const uint64_t ix = (uint64_t)rm64_bits(x);
+  uint32_t abstop = (uint32_t)(ix >> 52) & 0x7ffu;
+  if (abstop - 0x3c9u > 0x3eu) {                     // |x| < 2^-54 or |x| >= 512 or not finite
+    if (abstop < 0x3c9u) return 1.0 + x;             // tiny
+    if (abstop >= 0x409u) {                          // |x| >= 1024, inf, NaN
+      if (ix == 0xfff0000000000000ull) return 0.0;   // -inf
+      if (abstop >= 0x7ffu) return 1.0 + x;          // +inf, NaN
+      if (ix >> 63) return 0.0;                      // underflow (upstream: __math_uflow)
+      return rm64_fallback_exp(x);                   // overflow
+    }
+    abstop = 0;                                      // 512 <= |x| < 1024: the result may be subnormal
+  }
+  const double kd0 = fma(x, RM64_EXP_INVLN2N, RM64_EXP_SHIFT);
+  const uint64_t ki = (uint64_t)rm64_bits(kd0);
+  const double kd = kd0 - RM64_EXP_SHIFT;
+  double r = fma(kd, RM64_EXP_NEGLN2HIN, x);
+  r = fma(kd, RM64_EXP_NEGLN2LON, r);
+  const int idx = 2 * (int)(ki & 127u);
+  const uint64_t top = ki << 45;
+  const double tail = rm64_from_bits(rm64_exp_tab[idx]);
+  uint64_t sbits = rm64_exp_tab[idx + 1] + top;
+  const double r2 = r * r;
+  const double p23 = fma(r, RM64_EXP_C3, RM64_EXP_C2);
+  const double p45 = fma(r, RM64_EXP_C5, RM64_EXP_C4);
+  const double tmp = fma(r2 * r2, p45, fma(p23, r2, r + tail));
+  if (abstop == 0) {
+    // specialcase (e_exp.c): only the k < 0 branch can occur for the negative arguments of the cost term
+    if ((ki & 0x80000000u) == 0) return rm64_fallback_exp(x);
+    sbits += 1022ull << 52;
+    const double scale = rm64_from_bits(sbits);
+    const double st = tmp * scale;
+    double y = scale + st;
+    if (y < 1.0) {
+      const double hi = y + 1.0;
+      double lo = (scale - y) + st;
+      lo = ((1.0 - hi) + y) + lo;
+      y = (lo + hi) - 1.0;
+      if (y == 0.0) y = 0.0;
+    }
+    return 0x1p-1022 * y;
+  }
+  const double scale = rm64_from_bits(sbits);
+  return fma(scale, tmp, scale);
+}

@@ -22,8 +22,8 @@ def rel_err(got, want):
 
 
 def assert_rollouts_match(got, want, what="", exact=True):
-    """Discrete outputs exactly; states and costs bit-equal (exact=True: everything but the exp() of the exact-distance
-    cost runs through restated glibc routines or IEEE-exact operations) or within REL_TOL."""
+    """Discrete outputs exactly; states and costs bit-equal (exact=True, the default: every operation is IEEE-exact or a restated
+    glibc routine) or within REL_TOL."""
     d = got[:, DISC] != want[:, DISC]
     assert not d.any(), f"{what}: discrete outputs differ in rows {np.where(d.any(1))[0][:10]}"
     e = rel_err(got[:, CONT], want[:, CONT])

@@ -47,5 +47,19 @@ int main(int argc, char** argv) {
   long bad_sp = 0;
   for (double x : sp) bad_sp += !same(ref_sin(x), sin(x)) + !same(ref_cos(x), cos(x)) + (fabs(x) <= 0.787 ? !same(ref_tan(x), tan(x)) : 0);
   printf("special: %ld mismatches\n", bad_sp);
-  return (bad_sin || bad_cos || bad_sc || bad_tan || bad_sp) ? 1 : 0;
+  // exp over the cost term's arguments (-W3 * Dobs <= 0) and a band of positive ones
+  const Range er[] = {{1e-20, 1e-15, true}, {1e-15, 1e-3, true}, {1e-3, 1.0, true}, {1.0, 700.0, false}, {700.0, 1100.0, false}};
+  long bad_exp = 0, te = 0;
+  for (const Range& r : er)
+    for (long i = 0; i < n; i++) {
+      double x = -(r.logscale ? exp(uni(log(r.lo), log(r.hi))) : uni(r.lo, r.hi));
+      if ((rng() & 7) == 0 && x > -500.0) x = -x;
+      const double e = ref_exp(x);
+      if (!same(e, exp(x))) { if (bad_exp++ < 5) printf("  exp(%a): %a vs libm %a\n", x, e, exp(x)); }
+      te++;
+    }
+  const double se[] = {0.0, -0.0, -745.0, -745.2, -744.9, -708.4, -1023.9, -1024.0, -1e9, -INFINITY, 1e-300, -1e-300, -511.9999, -512.0};
+  for (double x : se) bad_exp += !same(ref_exp(x), exp(x));
+  printf("exp: %ld mismatches of %ld\n", bad_exp, te);
+  return (bad_sin || bad_cos || bad_sc || bad_tan || bad_sp || bad_exp) ? 1 : 0;
 }

@@ -141,7 +141,7 @@ def test_exact_distance_mode_vs_oracle(clrrt, planner):
     pl.set_obstacles(obs)
     pl.tree_reset_records(tree)
     got = clrrt.rollouts_as_table(pl.propagate_batch(par, smp))
-    assert_rollouts_match(got, want, "exact distance", exact=False)  # costS holds exp(-W3 Dobs): CUDA's exp, not glibc's
+    assert_rollouts_match(got, want, "exact distance")  # costS holds exp(-W3 Dobs): glibc's exp restated (refmath64.cuh)
     assert (want[:, 11] > 0).any()
     pl.close()
     orc.set_weights([10, 5, 0, 4, 1])

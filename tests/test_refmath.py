@@ -20,7 +20,7 @@ def test_refmath_matches_glibc(tmp_path):
 
 
 def test_refmath64_matches_glibc(tmp_path):
-    """cl-rrt_b200/csrc/refmath64.cuh (double sin / cos / tan of the rollout kernels) against the C library, bit for bit:
+    """cl-rrt_b200/csrc/refmath64.cuh (double sin / cos / tan / exp of the rollout kernels) against the C library, bit for bit:
     2 M random arguments per range here; 1.05e9 (sin, cos) and 7.5e8 (tan) when the header was written: 0 mismatches."""
     exe = str(tmp_path / "refmath64_sweep")
     subprocess.check_call(["g++", "-O2", "-mfma", "-ffp-contract=off", "-DREFMATH_HOST", "-o", exe,
@@ -28,5 +28,5 @@ def test_refmath64_matches_glibc(tmp_path):
     out = subprocess.run([exe, "2"], capture_output=True, text=True)
     print(out.stdout)
     assert out.returncode == 0, out.stdout
-    for name in ("sin", "cos", "sincos", "tan", "special"):
+    for name in ("sin", "cos", "sincos", "tan", "special", "exp"):
         assert f"{name}: 0 mismatches" in out.stdout
