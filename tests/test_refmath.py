@@ -30,3 +30,14 @@ def test_refmath64_matches_glibc(tmp_path):
     assert out.returncode == 0, out.stdout
     for name in ("sin", "cos", "sincos", "tan", "special", "exp"):
         assert f"{name}: 0 mismatches" in out.stdout
+
+
+def test_refmath64_tables_are_the_installed_libms():
+    """The lookup tables compiled into the kernels (csrc/refmath64_tables.inc) are those of this host's glibc: the generator
+    re-reads them from libm.so.6 and compares.  (On another glibc build the generator's own address checks fail first.)"""
+    import sys
+    if not os.path.exists("/lib/x86_64-linux-gnu/libm.so.6"):
+        import pytest
+        pytest.skip("no x86-64 glibc libm at the expected path")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "gen_refmath64_tables.py"), "--check"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
