@@ -81,7 +81,8 @@ class CpuPlanner:
         self._f("set_road")(C.c_int(int(bend)), _ptr(c), C.c_double(lane_shift))
 
     def set_tie_mode(self, mode):
-        """oracle only: 0 = equal keys ordered by node id (the product's rule), 1 = libstdc++ std::sort order."""
+        """oracle only: 0 = equal keys ordered by node id (the product's rule for batched searches), 1 = libstdc++ std::sort order
+        (the reference's, and the product's for single-sample searches)."""
         self._f("set_tie_mode")(C.c_int(mode))
 
     def set_weights(self, w5):

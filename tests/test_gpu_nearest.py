@@ -117,3 +117,42 @@ def test_spatial_orders_agree_on_a_large_tree(clrrt, golden_dir):
                 assert np.array_equal(a, b), f"mode {mode}"
     finally:
         pl.close()
+
+
+def test_equal_keys_follow_std_sort_for_single_sample_searches(clrrt, planner, golden_dir):
+    """A tree with exact copies of some nodes (equal keys by construction, as carried-over trees produce them): searched
+    one sample at a time, the candidate lists must equal the oracle's in BOTH tie rules — tie_mode 1 (default): the order
+    libstdc++'s std::sort leaves (the oracle restates its introsort, pinned against the reference binary); tie_mode 0:
+    lower node id first.  Batched searches always use the node-id rule."""
+    g = np.load(os.path.join(golden_dir, "g2_nearest.npz"))
+    car, goal = (0, 0, 0, 0, 3, 0), (50, 0, 0, 0)
+    base = g["tree"][:120]
+    dup = base[[7, 7, 30, 55, 55, 55, 90]].copy()      # copies of nodes, appended with new ids
+    tree = np.concatenate([base, dup])
+    smp, heu = g["samples"][:200], g["heuristic"][:200]
+    planner.set_query(car, goal, 5.0)
+    planner.tree_reset_records(tree)
+    orc = CpuPlanner("oracle")
+    orc.tree_init(car, goal, 5.0)
+    orc.tree_import(tree)
+    differ = 0
+    try:
+        lists = {}
+        for mode in (1, 0):
+            planner.set_tie_mode(mode)
+            orc.set_tie_mode(mode)
+            oc, ok, on = orc.nearest_batch(smp, heu)
+            got = [planner.nearest_batch(smp[j:j + 1], heu[j:j + 1]) for j in range(len(smp))]
+            gc = np.concatenate([x[0] for x in got]); gk = np.concatenate([x[1] for x in got]); gn = np.concatenate([x[2] for x in got])
+            assert np.array_equal(gn, on) and np.array_equal(gk, ok)
+            assert np.array_equal(gc, oc), f"tie mode {mode}: candidate order differs from the oracle's"
+            lists[mode] = gc
+        differ = int((lists[0] != lists[1]).any(1).sum())
+        # batched search: node-id rule whatever the mode
+        planner.set_tie_mode(1)
+        bc, bk, bn = planner.nearest_batch(smp, heu)
+        assert np.array_equal(bc, lists[0])
+    finally:
+        planner.set_tie_mode(1)
+    assert planner.tie_sorts() > 0
+    print(f"equal keys: {differ} of {len(smp)} lists differ between the two tie rules; {planner.tie_sorts()} searches repeated std::sort on the host")
