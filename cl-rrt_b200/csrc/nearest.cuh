@@ -13,7 +13,9 @@
 #include "common.cuh"
 #include "refmath.cuh"
 
-#define NEAREST_WARPS 8
+#ifndef NEAREST_WARPS
+#define NEAREST_WARPS 8   // samples per block (16 measured: 1.12 against 1.10 ms on C3)
+#endif
 #define NEAREST_THREADS (NEAREST_WARPS * 32)
 #define NEAREST_TILE 256
 
