@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CLRRT_LIB") or os.path.join(_HERE, "libclrrt_b200.so")  # CLRRT_LIB: kernel-tuning builds only
 SORT_LIMIT = 10
 RECORD_BYTES = 160
+COMM_ID_BYTES = 128
 
 
 class Vehicle(C.Structure):
@@ -36,7 +37,7 @@ class RoundStats(C.Structure):
     _fields_ = [("samples", C.c_int32), ("rollouts", C.c_int32), ("nodes_added", C.c_int32),
                 ("goal_nodes_added", C.c_int32), ("tree_size", C.c_int32), ("reserved", C.c_int32),
                 ("sim_steps", C.c_int64), ("ms_nearest", C.c_float), ("ms_rollout", C.c_float),
-                ("ms_prepare", C.c_float), ("ms_append", C.c_float)]
+                ("ms_prepare", C.c_float), ("ms_append", C.c_float), ("ms_exchange", C.c_float), ("nodes_local", C.c_int32)]
 
 
 class Counters(C.Structure):
@@ -101,9 +102,26 @@ def load_library():
     lib.clrrt_set_nearest_mode.argtypes = [vp, ip]
     lib.clrrt_tree_download_range.argtypes = [vp, ip, ip, vp]
     lib.clrrt_draw_samples.argtypes = [vp, ip, vp, vp]
+    lib.clrrt_comm_unique_id.argtypes = [vp, ip]
+    lib.clrrt_comm_init.argtypes = [vp, vp, ip, ip, ip]
+    lib.clrrt_comm_attach.argtypes = [vp, vp, ip, ip]
+    lib.clrrt_counters_get_global.argtypes = [vp, C.POINTER(Counters)]
+    lib.clrrt_tree_digest.argtypes = [vp, ip, ip, vp]
+    lib.clrrt_simulate.argtypes = [vp, vp, vp, vp, vp, ip, ip, ip, ip, dp, vp, vp, ip]
+    lib.clrrt_simulate_batch.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ip]
+    lib.clrrt_collide_batch.argtypes = [vp, vp, ip, vp, vp]
     lib.srand = C.CDLL(None).srand
     _lib = lib
     return lib
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the library: rank 0 calls it and hands the bytes to the other ranks."""
+    buf = (C.c_char * COMM_ID_BYTES)()
+    rc = load_library().clrrt_comm_unique_id(buf, COMM_ID_BYTES)
+    if rc != 0:
+        raise ClrrtError(f"clrrt_comm_unique_id failed ({rc}): NCCL not available")
+    return bytes(buf)
 
 
 def default_params():
@@ -307,6 +325,49 @@ class Planner:
             return out, traj, ref
         return (out, traj) if traj_stride else out
 
+    def simulate(self, state10, ref_x, ref_y, ref_v=None, goal_biased=False, gen_profile=True, vstart=0.0, ref_dir=1,
+                 traj_stride=0):
+        """Simulation::Simulation(RRT, state, ref, veh, GoalBiased, genProfile, Vstart) (rrt/include/rrt/simulation.h:18-19)
+        on a caller-owned reference.  Returns (rollout record, ref_v [filled when gen_profile], traj or None)."""
+        st = np.ascontiguousarray(state10, dtype=np.float64)
+        x = np.ascontiguousarray(ref_x, dtype=np.float64)
+        y = np.ascontiguousarray(ref_y, dtype=np.float64)
+        v = np.zeros(len(x)) if ref_v is None else np.array(ref_v, dtype=np.float64)
+        out = np.zeros(1, ROLLOUT_DTYPE)
+        traj = np.zeros((traj_stride, 10)) if traj_stride else None
+        self._ck(self.lib.clrrt_simulate(self.h, st.ctypes.data, x.ctypes.data, y.ctypes.data, v.ctypes.data, len(x), int(ref_dir),
+                                         int(bool(goal_biased)), int(bool(gen_profile)), float(vstart), out.ctypes.data,
+                                         None if traj is None else traj.ctypes.data, traj_stride))
+        return out[0], v, traj
+
+    def simulate_batch(self, states, refs, goal_biased=None, gen_profile=None, vstart=None, ref_dir=None):
+        """M rollouts with ragged references: refs = list of (x, y[, v]) arrays.  Returns (records, list of ref_v)."""
+        M = len(refs)
+        st = np.ascontiguousarray(states, dtype=np.float64).reshape(M, 10)
+        off = np.zeros(M + 1, np.int32)
+        off[1:] = np.cumsum([len(r[0]) for r in refs])
+        x = np.concatenate([np.asarray(r[0], float) for r in refs])
+        y = np.concatenate([np.asarray(r[1], float) for r in refs])
+        v = np.concatenate([np.asarray(r[2], float) if len(r) > 2 and r[2] is not None else np.zeros(len(r[0])) for r in refs])
+        gb = np.zeros(M, np.uint8) if goal_biased is None else np.ascontiguousarray(goal_biased, dtype=np.uint8)
+        gp = np.ones(M, np.uint8) if gen_profile is None else np.ascontiguousarray(gen_profile, dtype=np.uint8)
+        vs = np.zeros(M) if vstart is None else np.ascontiguousarray(vstart, dtype=np.float64)
+        dr = np.ones(M, np.int32) if ref_dir is None else np.ascontiguousarray(ref_dir, dtype=np.int32)
+        out = np.zeros(M, ROLLOUT_DTYPE)
+        self._ck(self.lib.clrrt_simulate_batch(self.h, M, st.ctypes.data, off.ctypes.data, x.ctypes.data, y.ctypes.data,
+                                               v.ctypes.data, gb.ctypes.data, gp.ctypes.data, vs.ctypes.data, dr.ctypes.data,
+                                               out.ctypes.data, None, 0))
+        return out, [v[off[i]:off[i + 1]] for i in range(M)]
+
+    def collide_batch(self, poses_xytht, want_distance=False):
+        """checkObsDistance for n poses (x, y, theta, t): verdict (1 = collision) from the verdict-only path and, on
+        request, the reference's pseudo-distance from the exact path."""
+        p = np.ascontiguousarray(poses_xytht, dtype=np.float64).reshape(-1, 4)
+        v = np.zeros(len(p), np.int32)
+        d = np.zeros(len(p)) if want_distance else None
+        self._ck(self.lib.clrrt_collide_batch(self.h, p.ctypes.data, len(p), v.ctypes.data, None if d is None else d.ctypes.data))
+        return (v, d) if want_distance else v
+
     def expand_round(self, samples, heuristic):
         s = np.ascontiguousarray(samples, dtype=np.float64).reshape(-1, 2)
         h = np.ascontiguousarray(heuristic, dtype=np.uint8)
@@ -331,7 +392,26 @@ class Planner:
         return dict(fail_collision=c.fail_collision, fail_acclimit=c.fail_acclimit,
                     fail_iterlimit=c.fail_iterlimit, sim_count=c.sim_count, rollouts=c.rollouts)
 
-    # ---- multi-GPU exchange ---------------------------------------------------------------------------
+    # ---- multi-GPU inside the library (clrrt_comm_*) ------------------------------------------------------
+    def comm_init(self, unique_id, rank, world):
+        """ncclCommInitRank on this context's device (collective).  unique_id: the 128 bytes of comm_unique_id()."""
+        buf = (C.c_char * COMM_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        self._ck(self.lib.clrrt_comm_init(self.h, buf, COMM_ID_BYTES, rank, world))
+
+    def counters_global(self):
+        c = Counters()
+        self._ck(self.lib.clrrt_counters_get_global(self.h, C.byref(c)))
+        return dict(fail_collision=c.fail_collision, fail_acclimit=c.fail_acclimit,
+                    fail_iterlimit=c.fail_iterlimit, sim_count=c.sim_count, rollouts=c.rollouts)
+
+    def tree_digest(self, first=0, count=None):
+        """128-bit order-sensitive digest of tree nodes [first, first + count) as a hex string."""
+        count = self.tree_size() - first if count is None else count
+        out = (C.c_uint64 * 2)()
+        self._ck(self.lib.clrrt_tree_digest(self.h, first, count, out))
+        return f"{out[0]:016x}{out[1]:016x}"
+
+    # ---- multi-GPU exchange, lower-level form -------------------------------------------------------------
     def set_defer_append(self, defer):
         self._ck(self.lib.clrrt_set_defer_append(self.h, int(defer)))
 

@@ -13,7 +13,9 @@
 #include "common.cuh"
 #include "nearest.cuh"
 #include "rollout.cuh"
+#include "simulate.cuh"
 #include "tree.cuh"
+#include "exchange.cuh"
 
 namespace {
 
@@ -87,7 +89,13 @@ struct clrrt_ctx {
   int32_t* h_ints = nullptr;                 // pinned
   unsigned long long* h_counters = nullptr;  // pinned
   RolloutScratch batch;
-  cudaEvent_t ev[6]{};
+  // multi-GPU exchange (exchange.cuh): one context per rank, tree replicated, samples sharded
+  ncclComm_t comm = nullptr;
+  bool own_comm = false;
+  int rank = 0, world = 1;
+  int32_t *d_counts = nullptr, *h_counts = nullptr;  // per-rank record counts of the round (device / pinned host)
+  NodeRecord* d_gather = nullptr;                    // [world][2 * max_round] gathered records
+  cudaEvent_t ev[7]{};
   int num_sms = 0, blocks_per_sm_main = 1, blocks_per_sm_gb = 1;
   size_t smem_bytes = 0;
   int refill_min = 4;  // idle lanes a warp accumulates before fetching work (C3 at 8 warps/SM: 4: 3.99, 8: 4.02, 12: 4.06, 16: 4.18 ms)
@@ -100,8 +108,20 @@ struct clrrt_ctx {
 
 namespace {
 
+// The parameter block c_prm is ONE __constant__ symbol per process and device.  Every entry point that launches kernels
+// re-uploads it when another context used it last (ensure_params) and synchronises its stream before returning, so
+// contexts may be interleaved freely from one thread; concurrent calls from several threads (even on distinct
+// contexts of one device) must be serialised by the caller — the reference is single-threaded too (include/clrrt.h).
 const clrrt_ctx* g_const_owner = nullptr;  // which context last uploaded c_prm on this process
 
+#define NCK(call)                                                                                         \
+  do {                                                                                                    \
+    ncclResult_t r_ = (call);                                                                             \
+    if (r_ != ncclSuccess) {                                                                              \
+      ctx->err = std::string(#call) + ": " + nc->GetErrorString(r_);                                      \
+      return CLRRT_ERR_CUDA;                                                                              \
+    }                                                                                                     \
+  } while (0)
 #define CK(call)                                                                                          \
   do {                                                                                                    \
     cudaError_t e_ = (call);                                                                              \
@@ -145,6 +165,7 @@ void fill_dev_params(clrrt_ctx* ctx) {
   d.n_static = keep.n_static; d.n_moving = keep.n_moving; d.static_in_smem = keep.static_in_smem;
   d.grid_nx = keep.grid_nx; d.grid_ny = keep.grid_ny; d.grid_inv_cell = keep.grid_inv_cell;
   d.grid_ox = keep.grid_ox; d.grid_oy = keep.grid_oy; d.pose_sub = keep.pose_sub; d.pose_nh = keep.pose_nh;
+  d.fine_margin = keep.fine_margin; d.deep_margin = keep.deep_margin;  // computed by clrrt_set_obstacles from the scene
   d.dmax = p.veh.dmax; d.ddmax = p.veh.ddmax; d.inv_Td = 1 / p.veh.Td; d.inv_Ta = 1 / p.veh.Ta;
   d.amin = p.veh.amin; d.amax = p.veh.amax; d.L = p.veh.L; d.Vch = p.veh.Vch; d.Kus = p.veh.Kus;
   d.sim_dt = p.sim_dt; d.mindla = p.ctrl_mindla; d.tla = p.ctrl_tla;
@@ -203,8 +224,11 @@ template <typename R> int configure_launch_t(clrrt_ctx* ctx) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rollout_kernel<R, 2, false, true>, ROLLOUT_THREADS, ctx->smem_bytes));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, rollout_kernel<R, 2, false, false>, ROLLOUT_THREADS, ctx->smem_bytes));
   }
-  ctx->blocks_per_sm_main = std::max(1, b0);
-  ctx->blocks_per_sm_gb = std::max(1, b1);
+  // the scratch records of goal-biased continuations (d_init, one per thread of the persistent grid) are sized for
+  // ROLLOUT_MAX_THREADS_PER_SM resident threads per SM
+  const int cap = std::max(1, ROLLOUT_MAX_THREADS_PER_SM / ROLLOUT_THREADS);
+  ctx->blocks_per_sm_main = std::min(cap, std::max(1, b0));
+  ctx->blocks_per_sm_gb = std::min(cap, std::max(1, b1));
   return CLRRT_OK;
 }
 
@@ -322,7 +346,7 @@ int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_r
       ctx->d_tile_vhi = reinterpret_cast<float*>(take((n8 / NEAREST_TILE + 8) * 4));
     }
   }
-  ctx->init_stride = ((K * CLRRT_SORT_LIMIT + (size_t)ctx->num_sms * 4 * ROLLOUT_THREADS) + 31) & ~(size_t)31;
+  ctx->init_stride = ((K * CLRRT_SORT_LIMIT + (size_t)ctx->num_sms * ROLLOUT_MAX_THREADS_PER_SM) + 31) & ~(size_t)31;
   ok &= mal(&ctx->d_init, ctx->init_stride * LANE_INIT_BYTES_PER_RECORD);
   ok &= mal((void**)&ctx->d_slot, K * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_res_code, K * CLRRT_SORT_LIMIT);
@@ -360,6 +384,10 @@ int clrrt_destroy(clrrt_ctx* ctx) {
                   ctx->d_records, ctx->d_counters, ctx->d_timeline, ctx->d_all_key, ctx->d_all_feas, ctx->batch.d_parent, ctx->batch.d_gb,
                   ctx->batch.d_samples, ctx->batch.d_out, ctx->batch.d_traj, ctx->batch.d_ref};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (ctx->comm && ctx->own_comm) { const NcclApi* nc = nccl_api(nullptr); if (nc) nc->CommDestroy(ctx->comm); }
+  if (ctx->d_counts) cudaFree(ctx->d_counts);
+  if (ctx->d_gather) cudaFree(ctx->d_gather);
+  if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
   if (ctx->h_ints) cudaFreeHost(ctx->h_ints);
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -375,7 +403,7 @@ int clrrt_get_device(const clrrt_ctx* ctx) { return ctx ? ctx->device : CLRRT_ER
 int clrrt_set_params(clrrt_ctx* ctx, const clrrt_params* p) {
   if (!ctx || !p) return CLRRT_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  const bool mode_changed = (ctx->prm.fp32 != 0) != (p->fp32 != 0);
+  const bool mode_changed = (ctx->prm.fp32 != 0) != (p->fp32 != 0) || (ctx->prm.Wcost[2] != 0.0) != (p->Wcost[2] != 0.0);
   ctx->prm = *p;
   fill_dev_params(ctx);
   if (mode_changed) {
@@ -521,6 +549,7 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
     void* old[] = {ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_bnd};
     for (void* q : old) if (q) cudaFree(q);
     ctx->d_hot = nullptr; ctx->d_cold = nullptr; ctx->d_mov = nullptr; ctx->d_bnd = nullptr;
+    ctx->obs_cap = 0;  // a failed allocation below must not leave the old capacity with null tables
     CK(cudaMalloc((void**)&ctx->d_hot, total * sizeof(ObsHot)));
     CK(cudaMalloc((void**)&ctx->d_cold, total * sizeof(ObsCold)));
     CK(cudaMalloc((void**)&ctx->d_mov, total * sizeof(ObsMoving)));
@@ -529,13 +558,13 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
   }
   if (cell_start.size() > ctx->cell_start_cap) {
     if (ctx->d_cell_start) cudaFree(ctx->d_cell_start);
-    ctx->d_cell_start = nullptr;
+    ctx->d_cell_start = nullptr; ctx->cell_start_cap = 0;
     CK(cudaMalloc((void**)&ctx->d_cell_start, cell_start.size() * sizeof(int32_t)));
     ctx->cell_start_cap = cell_start.size();
   }
   if (cell_items.size() + 8 > ctx->cell_items_cap) {
     if (ctx->d_cell_items) cudaFree(ctx->d_cell_items);
-    ctx->d_cell_items = nullptr;
+    ctx->d_cell_items = nullptr; ctx->cell_items_cap = 0;
     CK(cudaMalloc((void**)&ctx->d_cell_items, (cell_items.size() + 8) * sizeof(uint16_t)));
     ctx->cell_items_cap = cell_items.size() + 8;
   }
@@ -560,7 +589,7 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
     if ((double)cells <= 2.0e6) {
       if (cells > ctx->pose_cap) {
         if (ctx->d_pose_cells) cudaFree(ctx->d_pose_cells);
-        ctx->d_pose_cells = nullptr;
+        ctx->d_pose_cells = nullptr; ctx->pose_cap = 0;
         CK(cudaMalloc((void**)&ctx->d_pose_cells, cells * sizeof(uint4)));
         ctx->pose_cap = cells;
       }
@@ -586,6 +615,10 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
 int clrrt_tree_reset(clrrt_ctx* ctx, const clrrt_node* host, int n) {
   if (!ctx || !host || n < 1) return CLRRT_ERR_ARG;
   if (n > ctx->cap) return CLRRT_ERR_CAPACITY;
+  // parents precede their children (initializeTree builds a chain, rrtplanner.cpp:90-93): -1 <= parent < i, so that
+  // clrrt_best_path's walk over the parent array terminates inside the tree
+  for (int i = 0; i < n; i++)
+    if (host[i].parent < -1 || host[i].parent >= i) { ctx->err = "clrrt_tree_reset: node " + std::to_string(i) + " has parent " + std::to_string(host[i].parent); return CLRRT_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
   // route through the record path so that derived fields are produced by the same kernel as for appended nodes
   std::vector<NodeRecord> rec((size_t)n);
@@ -842,12 +875,118 @@ int clrrt_propagate_batch_ex(clrrt_ctx* ctx, const int32_t* parent, const double
   return CLRRT_OK;
 }
 
+// == Simulation::Simulation(RRT, state, ref, veh, GoalBiased, genProfile, Vstart), rrt/include/rrt/simulation.h:18-19
+int clrrt_simulate_batch(clrrt_ctx* ctx, int M, const double* state10, const int32_t* ref_offset, const double* ref_x,
+                         const double* ref_y, double* ref_v, const uint8_t* goal_biased, const uint8_t* gen_profile,
+                         const double* Vstart, const int32_t* ref_dir, clrrt_rollout* out, double* traj, int traj_stride) {
+  if (!ctx || M < 1 || !state10 || !ref_offset || !ref_x || !ref_y || !ref_v || !gen_profile || !Vstart || !out) return CLRRT_ERR_ARG;
+  if (traj && traj_stride < 2) return CLRRT_ERR_ARG;
+  if (ref_offset[0] != 0) return CLRRT_ERR_ARG;
+  for (int i = 0; i < M; i++) {
+    // upstream asserts at least three reference points (reference.cpp:19, :67) and reads three in getLateralError
+    if (ref_offset[i + 1] - ref_offset[i] < 3) { ctx->err = "clrrt_simulate: a reference needs at least 3 points"; return CLRRT_ERR_ARG; }
+    if (ref_dir && ref_dir[i] != 1 && ref_dir[i] != -1) { ctx->err = "clrrt_simulate: ref.dir must be +1 or -1"; return CLRRT_ERR_ARG; }
+  }
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_params(ctx);
+  if (rc) return rc;
+  const size_t npts = (size_t)ref_offset[M];
+  const size_t traj_elems = traj ? (size_t)M * traj_stride * 10 : 0;
+  // one scratch allocation per call: this is the fidelity entry point, not the throughput path
+  const size_t b_state = (size_t)M * 80, b_off = ((size_t)M + 1) * 4, b_pts = npts * 8, b_flag = (size_t)M, b_vs = (size_t)M * 8,
+               b_dir = (size_t)M * 4, b_out = (size_t)M * sizeof(clrrt_rollout);
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t total = al(b_state) + al(b_off) + 3 * al(b_pts) + 2 * al(b_flag) + al(b_vs) + al(b_dir) + al(b_out) + al(traj_elems * 8);
+  unsigned char* base = nullptr;
+  CK(cudaMalloc((void**)&base, total));
+  unsigned char* q = base;
+  auto take = [&](size_t b) { unsigned char* r = q; q += al(b); return r; };
+  double* d_state = (double*)take(b_state); int32_t* d_off = (int32_t*)take(b_off);
+  double* d_x = (double*)take(b_pts); double* d_y = (double*)take(b_pts); double* d_v = (double*)take(b_pts);
+  uint8_t* d_gb = (uint8_t*)take(b_flag); uint8_t* d_gp = (uint8_t*)take(b_flag);
+  double* d_vs = (double*)take(b_vs); int32_t* d_dir = (int32_t*)take(b_dir);
+  clrrt_rollout* d_out = (clrrt_rollout*)take(b_out); double* d_traj = (double*)take(traj_elems * 8);
+  std::vector<uint8_t> gbf((size_t)M, 0);
+  if (goal_biased) for (int i = 0; i < M; i++) gbf[i] = goal_biased[i] ? 1 : 0;
+  cudaStream_t st = ctx->stream;
+  auto fail = [&](cudaError_t e, const char* what) { ctx->err = std::string(what) + ": " + cudaGetErrorString(e); cudaFree(base); return CLRRT_ERR_CUDA; };
+  cudaError_t e;
+#define SIM_CK(call) if ((e = (call)) != cudaSuccess) return fail(e, #call)
+  SIM_CK(cudaMemcpyAsync(d_state, state10, b_state, cudaMemcpyHostToDevice, st));
+  SIM_CK(cudaMemcpyAsync(d_off, ref_offset, b_off, cudaMemcpyHostToDevice, st));
+  SIM_CK(cudaMemcpyAsync(d_x, ref_x, b_pts, cudaMemcpyHostToDevice, st));
+  SIM_CK(cudaMemcpyAsync(d_y, ref_y, b_pts, cudaMemcpyHostToDevice, st));
+  SIM_CK(cudaMemcpyAsync(d_v, ref_v, b_pts, cudaMemcpyHostToDevice, st));  // used as is when genProfile is false
+  SIM_CK(cudaMemcpyAsync(d_gb, gbf.data(), b_flag, cudaMemcpyHostToDevice, st));
+  SIM_CK(cudaMemcpyAsync(d_gp, gen_profile, b_flag, cudaMemcpyHostToDevice, st));
+  SIM_CK(cudaMemcpyAsync(d_vs, Vstart, b_vs, cudaMemcpyHostToDevice, st));
+  if (ref_dir) SIM_CK(cudaMemcpyAsync(d_dir, ref_dir, b_dir, cudaMemcpyHostToDevice, st));
+  if (traj) SIM_CK(cudaMemsetAsync(d_traj, 0, traj_elems * 8, st));
+  SimJob job;
+  job.M = M; job.state10 = d_state; job.ref_off = d_off; job.rx = d_x; job.ry = d_y; job.rv = d_v; job.gb = d_gb; job.genp = d_gp;
+  job.vstart = d_vs; job.dir = ref_dir ? d_dir : nullptr; job.out = d_out; job.traj = traj ? d_traj : nullptr; job.traj_stride = traj_stride;
+  job.counters = ctx->d_counters;
+  const int blocks = (M + 127) / 128;
+  if (ctx->dprm.exact_dist)
+    simulate_kernel<true><<<blocks, 128, 0, st>>>(job, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells);
+  else
+    simulate_kernel<false><<<blocks, 128, 0, st>>>(job, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells);
+  SIM_CK(cudaGetLastError());
+  SIM_CK(cudaMemcpyAsync(out, d_out, b_out, cudaMemcpyDeviceToHost, st));
+  SIM_CK(cudaMemcpyAsync(ref_v, d_v, b_pts, cudaMemcpyDeviceToHost, st));
+  if (traj) SIM_CK(cudaMemcpyAsync(traj, d_traj, traj_elems * 8, cudaMemcpyDeviceToHost, st));
+  SIM_CK(cudaStreamSynchronize(st));
+#undef SIM_CK
+  cudaFree(base);
+  return CLRRT_OK;
+}
+
+int clrrt_simulate(clrrt_ctx* ctx, const double* state10, const double* ref_x, const double* ref_y, double* ref_v, int n_ref,
+                   int ref_dir, int goal_biased, int gen_profile, double Vstart, clrrt_rollout* out, double* traj, int traj_stride) {
+  if (n_ref < 3) return CLRRT_ERR_ARG;
+  const int32_t off[2] = {0, n_ref};
+  const uint8_t gb = goal_biased ? 1 : 0, gp = gen_profile ? 1 : 0;
+  const int32_t dir = ref_dir;
+  return clrrt_simulate_batch(ctx, 1, state10, off, ref_x, ref_y, ref_v, &gb, &gp, &Vstart, &dir, out, traj, traj_stride);
+}
+
+// == checkObsDistance(states, det, carState), rrt/src/old_collisioncheck.cpp:24-51, for n poses
+int clrrt_collide_batch(clrrt_ctx* ctx, const double* pose_xytht, int n, int32_t* verdict, double* dobs) {
+  if (!ctx || !pose_xytht || !verdict || n < 1) return CLRRT_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_params(ctx);
+  if (rc) return rc;
+  double* d_pose = nullptr; int32_t* d_v = nullptr; double* d_d = nullptr;
+  CK(cudaMalloc((void**)&d_pose, (size_t)n * 32));
+  cudaError_t e = cudaMalloc((void**)&d_v, (size_t)n * 4);
+  if (e == cudaSuccess && dobs) e = cudaMalloc((void**)&d_d, (size_t)n * 8);
+  auto done = [&](int code) { cudaFree(d_pose); if (d_v) cudaFree(d_v); if (d_d) cudaFree(d_d); return code; };
+  if (e != cudaSuccess) { ctx->err = std::string("clrrt_collide_batch: ") + cudaGetErrorString(e); return done(CLRRT_ERR_CUDA); }
+  cudaStream_t st = ctx->stream;
+  e = cudaMemcpyAsync(d_pose, pose_xytht, (size_t)n * 32, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    collide_batch_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_pose, n, d_v, d_d, ctx->d_bnd, ctx->d_hot, ctx->d_cold, ctx->d_mov,
+                                                         ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(verdict, d_v, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && dobs) e = cudaMemcpyAsync(dobs, d_d, (size_t)n * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { ctx->err = std::string("clrrt_collide_batch: ") + cudaGetErrorString(e); return done(CLRRT_ERR_CUDA); }
+  return done(CLRRT_OK);
+}
+
+// Records are in sample order, so when the tree is full the prefix that fits is appended (what the sequential
+// reference would have added first) and CLRRT_ERR_CAPACITY tells the caller to stop expanding.
 static int append_local(clrrt_ctx* ctx, const NodeRecord* d_rec, int n) {
   if (n <= 0) return CLRRT_OK;
-  if (ctx->n_tree + n > ctx->cap) { ctx->err = "tree capacity exceeded"; return CLRRT_ERR_CAPACITY; }
-  append_records_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->tree, ctx->n_tree, d_rec, n, ctx->cap);
-  CK(cudaGetLastError());
-  ctx->n_tree += n;
+  const int fit = std::min(n, ctx->cap - ctx->n_tree);
+  if (fit > 0) {
+    append_records_kernel<<<(fit + 255) / 256, 256, 0, ctx->stream>>>(ctx->tree, ctx->n_tree, d_rec, fit, ctx->cap);
+    CK(cudaGetLastError());
+    ctx->n_tree += fit;
+  }
+  if (fit < n) { ctx->err = "tree capacity exceeded: " + std::to_string(n - fit) + " accepted nodes dropped"; return CLRRT_ERR_CAPACITY; }
   return CLRRT_OK;
 }
 
@@ -911,14 +1050,45 @@ int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint
   pack_records_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(ctx->stage, ctx->d_valid, K, ctx->d_block_sums, ctx->d_records,
                                                          ctx->d_slot, K * CLRRT_SORT_LIMIT);
   CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev[6], st));
+  const bool exchange = ctx->world > 1 && !ctx->defer_append;
+  const NcclApi* nc = nullptr;
+  if (exchange) {
+    // per-round node all-gather (exchange.cuh): the ranks' record counts first — 4 bytes each, read back together with
+    // this rank's counters in the round's one host synchronisation
+    if (!(nc = nccl_api(&ctx->err))) return CLRRT_ERR_STATE;
+    NCK(nc->AllGather(ctx->d_ints + 3, ctx->d_counts, 1, ncclInt32, ctx->comm, st));
+    CK(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, (size_t)ctx->world * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  }
   CK(cudaMemcpyAsync(ctx->h_ints + 3, ctx->d_ints + 3, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   const int n_new = ctx->h_ints[3];
   ctx->last_records = n_new;
-  if (!ctx->defer_append) {
-    if ((rc = append_local(ctx, ctx->d_records, n_new))) return rc;
+  int n_added = n_new;
+  int rc_append = CLRRT_OK;  // a full tree still appends the prefix that fits and reports the round (see append_local)
+  if (exchange) {
+    int stride = 0;
+    long long total = 0;
+    for (int r = 0; r < ctx->world; r++) { stride = std::max(stride, ctx->h_counts[r]); total += ctx->h_counts[r]; }
+    n_added = (int)total;
+    if (total > 0) {
+      // the records at the stride of the largest chunk, then ONE append launch over all ranks' chunks in rank order
+      // (= global sample order, rrtplanner.cpp:150-173), chunk offsets from the gathered counts on the device
+      NCK(nc->AllGather(ctx->d_records, ctx->d_gather, (size_t)stride * sizeof(NodeRecord), ncclInt8, ctx->comm, st));
+      const int fit = (int)std::min<long long>(total, ctx->cap - ctx->n_tree);
+      if (fit > 0) {
+        append_gathered_kernel<<<(fit + 255) / 256, 256, 0, st>>>(ctx->tree, ctx->n_tree, ctx->d_gather, stride, ctx->d_counts,
+                                                                 ctx->world, fit, ctx->cap);
+        CK(cudaGetLastError());
+        ctx->n_tree += fit;
+      }
+      if (fit < total) { ctx->err = "tree capacity exceeded: " + std::to_string(total - fit) + " accepted nodes dropped"; rc_append = CLRRT_ERR_CAPACITY; }
+    }
+  } else if (!ctx->defer_append) {
+    rc_append = append_local(ctx, ctx->d_records, n_new);
   }
+  if (rc_append != CLRRT_OK && rc_append != CLRRT_ERR_CAPACITY) return rc_append;
   CK(cudaEventRecord(ctx->ev[4], st));
   CK(cudaEventSynchronize(ctx->ev[4]));
   if (stats) {
@@ -926,14 +1096,16 @@ int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint
     stats->samples = K;
     stats->rollouts = (int32_t)(ctx->h_counters[4] - ctx->h_counters[12]);
     stats->sim_steps = (int64_t)(ctx->h_counters[3] - ctx->h_counters[11]);
-    stats->nodes_added = n_new;
+    stats->nodes_added = n_added;
+    stats->nodes_local = n_new;
     stats->tree_size = ctx->n_tree;
     cudaEventElapsedTime(&stats->ms_nearest, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&stats->ms_prepare, ctx->ev[1], ctx->ev[5]);
     cudaEventElapsedTime(&stats->ms_rollout, ctx->ev[5], ctx->ev[2]);
     cudaEventElapsedTime(&stats->ms_append, ctx->ev[2], ctx->ev[4]);
+    cudaEventElapsedTime(&stats->ms_exchange, ctx->ev[6], ctx->ev[4]);
   }
-  return CLRRT_OK;
+  return rc_append;
 }
 
 int clrrt_expand_round(clrrt_ctx* ctx, const double* sample_xy, const uint8_t* heuristic, int K,
@@ -961,7 +1133,7 @@ int clrrt_best_path(clrrt_ctx* ctx, int32_t* ids, int cap, int* n_out) {
   std::vector<int32_t> par((size_t)ctx->n_tree);
   CK(cudaMemcpy(par.data(), ctx->tree.parent, (size_t)ctx->n_tree * 4, cudaMemcpyDeviceToHost));
   std::vector<int32_t> chain;
-  for (int id = best; id >= 0 && (int)chain.size() <= ctx->n_tree; id = par[id]) chain.push_back(id);
+  for (int id = best; id >= 0 && id < ctx->n_tree && (int)chain.size() <= ctx->n_tree; id = par[id]) chain.push_back(id);
   std::reverse(chain.begin(), chain.end());
   *n_out = (int)chain.size();
   for (int i = 0; i < std::min<int>(cap, (int)chain.size()); i++) ids[i] = chain[i];
@@ -1050,6 +1222,85 @@ int clrrt_append_records(clrrt_ctx* ctx, const void* d_records, const int32_t* c
     if (rc) return rc;
   }
   CK(cudaStreamSynchronize(ctx->stream));
+  return CLRRT_OK;
+}
+
+
+// ---- multi-GPU inside the library (exchange.cuh) -------------------------------------------------------------------
+int clrrt_comm_unique_id(void* id, int bytes) {
+  if (!id || bytes < (int)sizeof(ncclUniqueId)) return CLRRT_ERR_ARG;
+  const NcclApi* nc = nccl_api(nullptr);
+  if (!nc) return CLRRT_ERR_STATE;
+  ncclUniqueId u;
+  if (nc->GetUniqueId(&u) != ncclSuccess) return CLRRT_ERR_CUDA;
+  memcpy(id, &u, sizeof u);
+  return CLRRT_OK;
+}
+
+static int comm_buffers(clrrt_ctx* ctx) {
+  if (!ctx->d_counts) CK(cudaMalloc((void**)&ctx->d_counts, CLRRT_MAX_WORLD * sizeof(int32_t)));
+  if (!ctx->h_counts) CK(cudaMallocHost((void**)&ctx->h_counts, CLRRT_MAX_WORLD * sizeof(int32_t)));
+  if (ctx->d_gather) { cudaFree(ctx->d_gather); ctx->d_gather = nullptr; }
+  CK(cudaMalloc((void**)&ctx->d_gather, (size_t)ctx->world * 2 * (size_t)ctx->max_round * sizeof(NodeRecord)));
+  return CLRRT_OK;
+}
+
+int clrrt_comm_attach(clrrt_ctx* ctx, void* nccl_comm, int rank, int world) {
+  if (!ctx || !nccl_comm || world < 1 || world > CLRRT_MAX_WORLD || rank < 0 || rank >= world) return CLRRT_ERR_ARG;
+  if (!nccl_api(&ctx->err)) return CLRRT_ERR_STATE;
+  CK(cudaSetDevice(ctx->device));
+  ctx->comm = (ncclComm_t)nccl_comm; ctx->own_comm = false; ctx->rank = rank; ctx->world = world;
+  return comm_buffers(ctx);
+}
+
+int clrrt_comm_init(clrrt_ctx* ctx, const void* id, int bytes, int rank, int world) {
+  if (!ctx || !id || bytes < (int)sizeof(ncclUniqueId) || world < 1 || world > CLRRT_MAX_WORLD || rank < 0 || rank >= world) return CLRRT_ERR_ARG;
+  const NcclApi* nc = nccl_api(&ctx->err);
+  if (!nc) return CLRRT_ERR_STATE;
+  CK(cudaSetDevice(ctx->device));
+  ncclUniqueId u;
+  memcpy(&u, id, sizeof u);
+  ncclComm_t c = nullptr;
+  NCK(nc->CommInitRank(&c, world, u, rank));
+  ctx->comm = c; ctx->own_comm = true; ctx->rank = rank; ctx->world = world;
+  return comm_buffers(ctx);
+}
+
+int clrrt_comm_info(const clrrt_ctx* ctx, int* rank, int* world) {
+  if (!ctx) return CLRRT_ERR_ARG;
+  if (rank) *rank = ctx->rank;
+  if (world) *world = ctx->world;
+  return CLRRT_OK;
+}
+
+int clrrt_counters_get_global(clrrt_ctx* ctx, clrrt_counters* out) {
+  if (!ctx || !out) return CLRRT_ERR_ARG;
+  if (ctx->world == 1) return clrrt_counters_get(ctx, out);
+  const NcclApi* nc = nccl_api(&ctx->err);
+  if (!nc) return CLRRT_ERR_STATE;
+  CK(cudaSetDevice(ctx->device));
+  unsigned long long* tmp = ctx->d_counters + 24;  // scratch words of the counter block
+  NCK(nc->AllReduce(ctx->d_counters, tmp, 5, ncclUint64, ncclSum, ctx->comm, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_counters, tmp, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  out->fail_collision = (int64_t)ctx->h_counters[0]; out->fail_acclimit = (int64_t)ctx->h_counters[1];
+  out->fail_iterlimit = (int64_t)ctx->h_counters[2]; out->sim_count = (int64_t)ctx->h_counters[3];
+  out->rollouts = (int64_t)ctx->h_counters[4];
+  return CLRRT_OK;
+}
+
+int clrrt_tree_digest(clrrt_ctx* ctx, int first, int count, uint64_t out2[2]) {
+  if (!ctx || !out2 || first < 0 || count < 0 || first + count > ctx->n_tree) return CLRRT_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  unsigned long long* d = ctx->d_counters + 30;
+  CK(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  if (count > 0) {
+    tree_digest_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(ctx->tree, first, count, d);
+    CK(cudaGetLastError());
+  }
+  CK(cudaMemcpyAsync(ctx->h_counters + 14, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  out2[0] = ctx->h_counters[14]; out2[1] = ctx->h_counters[15];
   return CLRRT_OK;
 }
 

@@ -208,7 +208,10 @@ clrrt_round_stats expandTree(Vehicle&, MyRRT& RRT, int K) {
   std::vector<uint8_t> h((size_t)K);
   clrrt_draw_samples(RRT.goalPose.data(), K, s.data(), h.data());  // rrtplanner.cpp:133-143 on rand()
   clrrt_round_stats st;
-  ck(RRT.ctx(), clrrt_expand_round(RRT.ctx(), s.data(), h.data(), K, &st), "clrrt_expand_round");
+  const int rc = clrrt_expand_round(RRT.ctx(), s.data(), h.data(), K, &st);
+  // a full tree is not an error of the query: the round's prefix that fits was appended; the caller stops expanding
+  if (rc == CLRRT_ERR_CAPACITY) { RRT.treeFull = true; return st; }
+  ck(RRT.ctx(), rc, "clrrt_expand_round");
   return st;
 }
 
@@ -367,6 +370,7 @@ void MotionPlanner::planMotion(MotionRequest req) {
   RRT.setObstacles(det);                                        // :24
   RRT.carState = carPose;
   if (!params.commit_path) bestNodes.clear();                   // :28-30
+  RRT.treeFull = false;
   initializeTree(RRT, veh, bestNodes, carPose);                 // :32
   lastCarried = (int)RRT.carried().size();
   lastInitialTree = RRT.treeSize();
@@ -375,7 +379,8 @@ void MotionPlanner::planMotion(MotionRequest req) {
   for (;; iter++) {
     if (maxIterations >= 0) { if (iter >= maxIterations) break; }
     else if (std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() >= budget_ms) break;
-    expandTree(veh, RRT, samplesPerRound);
+    expandTree(veh, RRT, round);
+    if (RRT.treeFull) { iter++; break; }  // capacity reached: keep what was grown, extract the best path below
   }
   lastIterations = iter;
   lastTreeSize = RRT.treeSize();
@@ -399,11 +404,21 @@ void MotionPlanner::planMotion(MotionRequest req) {
 
 }  // namespace clrrt
 
+// text of the last failure of a clrrt_host_* call on this thread (the facade throws clrrt::Error; the C view catches it)
+static thread_local std::string g_host_error;
+extern "C" const char* clrrt_host_last_error(void) { return g_host_error.c_str(); }
+static int host_fail(const char* where, const std::exception& e) {
+  g_host_error = std::string(where) + ": " + e.what();
+  return CLRRT_ERR_STATE;
+}
+
 extern "C" int clrrt_host_plan_motion(const double* car_state6, const double* goal4, double vmax, const clrrt_obstacle* obs,
                                       int n_obs, int samples_per_round, int max_iterations, double budget_ms, unsigned seed,
                                       int device, int* tree_size, int* iterations, clrrt_counters* counters, double* traj8,
                                       int traj_cap, int* traj_len, int32_t* best_ids, int best_cap, int* best_len, double* remat_err) {
+  if (!car_state6 || !goal4 || n_obs < 0 || (n_obs > 0 && !obs)) { g_host_error = "clrrt_host_plan_motion: null argument"; return CLRRT_ERR_ARG; }
   try {
+    g_host_error.clear();
     clrrt::MotionPlanner mp;
     mp.device = device;
     mp.samplesPerRound = samples_per_round;
@@ -438,8 +453,7 @@ extern "C" int clrrt_host_plan_motion(const double* car_state6, const double* go
     if (remat_err) *remat_err = mp.lastRematError;
     return CLRRT_OK;
   } catch (const std::exception& e) {
-    fprintf(stderr, "clrrt_host_plan_motion: %s\n", e.what());
-    return CLRRT_ERR_STATE;
+    return host_fail("clrrt_host_plan_motion", e);
   }
 }
 
@@ -458,7 +472,9 @@ extern "C" void clrrt_host_planner_destroy(void* h) { delete static_cast<clrrt::
 extern "C" int clrrt_host_planner_query(void* h, const double* world_state6, const double* goal4, double vmax,
                                         const clrrt_obstacle* obs, int n_obs, int max_iterations, double budget_ms,
                                         int32_t* sizes4, double* best_cost, clrrt_counters* counters) {
+  if (!h || !world_state6 || !goal4 || n_obs < 0 || (n_obs > 0 && !obs)) { g_host_error = "clrrt_host_planner_query: null argument"; return CLRRT_ERR_ARG; }
   try {
+    g_host_error.clear();
     clrrt::MotionPlanner& mp = *static_cast<clrrt::MotionPlanner*>(h);
     mp.maxIterations = max_iterations;
     mp.budget_ms = budget_ms;
@@ -482,8 +498,7 @@ extern "C" int clrrt_host_planner_query(void* h, const double* world_state6, con
     if (counters) *counters = mp.lastCounters;
     return CLRRT_OK;
   } catch (const std::exception& e) {
-    fprintf(stderr, "clrrt_host_planner_query: %s\n", e.what());
-    return CLRRT_ERR_STATE;
+    return host_fail("clrrt_host_planner_query", e);
   }
 }
 // bestNodes of the last query (world frame): {state[10], ref front xy, ref back xy, ref.v.back(), costE, costS,

@@ -93,6 +93,7 @@ class MyRRT {
   std::vector<Obstacle2D> det;
   std::vector<double> carState;
   double Wcost[5];
+  bool treeFull = false;  // set by expandTree when a round hit the tree capacity (the fitting prefix was appended)
 
   MyRRT(const std::vector<double>& goalPose, const std::vector<double>& laneShifts, const std::vector<double>& Cxy,
         const bool& bend, const Vehicle& veh, const PlannerParams& prm, double vmax, double car_speed, int device = 0,

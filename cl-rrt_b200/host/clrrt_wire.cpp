@@ -159,7 +159,7 @@ std::vector<Path> getCommittedPath(std::vector<Node> bestPath, double& Tp, doubl
 // ---- flat entry points ---------------------------------------------------------------------------------------------
 extern "C" int clrrt_wire_parse_request(const uint8_t* buf, int n, double* goal4, double* vmax, int* bend, int* n_lane_shifts) {
   clrrt::MotionRequest m;
-  if (!buf || n < 0 || !clrrt::wire::deserialize(buf, (size_t)n, m) || m.goal.size() < 4) return CLRRT_ERR_ARG;
+  if (!buf || !goal4 || n < 0 || !clrrt::wire::deserialize(buf, (size_t)n, m) || m.goal.size() < 4) return CLRRT_ERR_ARG;
   for (int i = 0; i < 4; i++) goal4[i] = m.goal[i];
   if (vmax) *vmax = m.vmax;
   if (bend) *bend = m.bend ? 1 : 0;
@@ -168,7 +168,7 @@ extern "C" int clrrt_wire_parse_request(const uint8_t* buf, int n, double* goal4
 }
 extern "C" int clrrt_wire_parse_state(const uint8_t* buf, int n, double* state6) {
   std::vector<double> s;
-  if (!buf || n < 0 || !clrrt::wire::deserializeState(buf, (size_t)n, s) || s.size() != 6) return CLRRT_ERR_ARG;
+  if (!buf || !state6 || n < 0 || !clrrt::wire::deserializeState(buf, (size_t)n, s) || s.size() != 6) return CLRRT_ERR_ARG;
   for (int i = 0; i < 6; i++) state6[i] = s[i];
   return CLRRT_OK;
 }

@@ -10,7 +10,9 @@
  * Conventions: plain pointers and sizes only; every call returns 0 or a negative clrrt_status; nothing
  * is thrown across the boundary; the caller owns all host buffers, the context owns all device memory
  * and its stream; calls on one context are not thread-safe (the reference is single-threaded and keeps
- * its state in file-scope globals), distinct contexts are independent; one context per GPU.
+ * its state in file-scope globals).  Distinct contexts may be used alternately from one thread; calls from
+ * several threads of one process must be serialised by the caller even across contexts of the same GPU (the kernels'
+ * parameter block is one __constant__ symbol per device).  One context per GPU and process is the intended use.
  * There is NO CPU fallback: without a CUDA device clrrt_create fails with CLRRT_ERR_CUDA.
  */
 #ifndef CLRRT_H
@@ -109,6 +111,11 @@ typedef struct clrrt_round_stats {
   /* device time per phase (CUDA events on the ctx stream): candidate search; the rollout kernel alone; reference ends +
    * launch order before it; winner selection + compaction + append after it */
   float ms_nearest, ms_rollout, ms_prepare, ms_append;
+  /* multi-GPU (clrrt_comm_*): the exchange's share of ms_append (count + record all-gather and the append of all ranks'
+   * chunks); nodes_added then counts the nodes of ALL ranks, nodes_local this rank's, samples / rollouts / sim_steps this
+   * rank's shard */
+  float ms_exchange;
+  int32_t nodes_local;
 } clrrt_round_stats;
 
 typedef struct clrrt_ctx clrrt_ctx;
@@ -158,6 +165,33 @@ int clrrt_propagate_batch_ex(clrrt_ctx* ctx, const int32_t* parent, const double
                              const uint8_t* goal_biased, int M, clrrt_rollout* out, double* traj, int traj_stride,
                              double* ref_xyv, int ref_stride);
 
+/* == Simulation::Simulation(const MyRRT& RRT, const vector<double>& state, MyReference& ref, const Vehicle& veh,
+ *                           const bool& GoalBiased, const bool& genProfile, const double& Vstart)
+ * (rrt/include/rrt/simulation.h:18-19, rrt/src/simulation.cpp:36-143) with the reference's own parameter list: an ARBITRARY
+ * start state (10 entries, rrt/src/motionplanner.cpp:90 + the four logging slots) and a caller-owned reference path
+ * ref.x / ref.y of n_ref >= 3 points of any shape, ref_dir = MyReference::dir (+1 / -1).  gen_profile != 0 runs
+ * generateVelocityProfile and FILLS ref_v[0..n_ref) — the constructor mutates the caller's MyReference the same way
+ * (expandTree then stores that ref in the new Node, rrt/src/rrtplanner.cpp:156); gen_profile == 0 uses ref_v as given.
+ * RRT (goal, obstacles, weights) and veh are the context's.  out->state = stateArray.back(), out->fail / end_reached /
+ * goal_reached as clrrt_propagate_batch; traj (optional) receives stateArray, traj_stride x 10.  The failure counters
+ * advance as upstream (rrt/src/simulation.cpp:59, :85, :102, :142).  Out-of-bounds reads of the unmodified reference
+ * (ref.v[IDwp+2], ref.x[IDwp+1] near the end of the path) follow the index-clamped "defined" variant (out->tainted). */
+int clrrt_simulate(clrrt_ctx* ctx, const double* state10, const double* ref_x, const double* ref_y, double* ref_v, int n_ref,
+                   int ref_dir, int goal_biased, int gen_profile, double Vstart, clrrt_rollout* out, double* traj, int traj_stride);
+/* M of them in one launch: ragged references, rollout i uses points [ref_offset[i], ref_offset[i+1]) (ref_offset[0] == 0);
+ * goal_biased and ref_dir may be NULL (all 0 / all +1). */
+int clrrt_simulate_batch(clrrt_ctx* ctx, int M, const double* state10, const int32_t* ref_offset, const double* ref_x,
+                         const double* ref_y, double* ref_v, const uint8_t* goal_biased, const uint8_t* gen_profile,
+                         const double* Vstart, const int32_t* ref_dir, clrrt_rollout* out, double* traj, int traj_stride);
+
+/* == checkObsDistance(states, det, carState) (rrt/src/old_collisioncheck.cpp:24-51; the stub of rrt/src/collisioncheck.cpp
+ * when no obstacles are set) for n poses: pose_xytht[4 i ..] = states[0], states[1], states[2] (rear-axle x, y, heading) and
+ * states[6] (time, for moving obstacles).  verdict[i] = 1 when the reference returns 0 (collision) — computed by the
+ * product's verdict-only path (pose grid, three-way classification, float SAT only in the band around touching), the one
+ * every rollout step takes when Wcost[2] == 0.  dobs (optional): the value the reference returns, from the exact path
+ * (every obstacle's first separating axis in float, minimum tracked; 100 without obstacles). */
+int clrrt_collide_batch(clrrt_ctx* ctx, const double* pose_xytht, int n, int32_t* verdict, double* dobs);
+
 /* == K iterations of expandTree (rrt/src/rrtplanner.cpp:123-174) against ONE tree snapshot: candidate search,
  * rollouts in candidate order until the first success, goal-biased rollout from the node just added, append in
  * sample order.  K == 1 is the reference's sequential algorithm exactly. */
@@ -178,7 +212,29 @@ int clrrt_counters_get(clrrt_ctx* ctx, clrrt_counters* out);
  * sample in the reference's order: longitudinal, lateral, heuristic.  heuristic[j] = 0 explore (r <= 0.7), 1 optimize. */
 int clrrt_draw_samples(const double goal[4], int K, double* sample_xy, uint8_t* heuristic);
 
-/* Multi-GPU (one context per rank): after a round run with append deferred, the nodes accepted by this rank are
+/* Multi-GPU inside the library.  The reference is one process and one thread (expandTree,
+ * rrt/include/rrt/rrtplanner.h:87); here one context per GPU holds the full tree, clrrt_expand_round receives THIS RANK's
+ * contiguous shard of the round's samples (rank r: samples [r K/world, (r+1) K/world) of the global round), and before it
+ * returns the nodes accepted by all ranks are exchanged with ncclAllGather (record counts, then fixed-stride records, on the
+ * context's stream over NVLink) and appended in rank order = global sample order = the order of rrt/src/rrtplanner.cpp
+ * :150-173, so every rank ends each round with the same tree as a single-GPU round over all K samples.
+ *   clrrt_comm_unique_id: ncclGetUniqueId (rank 0 calls it and hands the 128 bytes to the other ranks by any channel);
+ *   clrrt_comm_init:      ncclCommInitRank on the context's device (collective: every rank calls it);
+ *   clrrt_comm_attach:    use a communicator the caller owns (ncclComm_t) instead.
+ * NCCL is bound at run time (libnccl.so.2); without it these return CLRRT_ERR_STATE and single-GPU use is unaffected.
+ * clrrt_counters_get_global: the failure counters summed over ranks (collective).  K = 1 sequential mode does not shard. */
+#define CLRRT_COMM_ID_BYTES 128
+int clrrt_comm_unique_id(void* id, int bytes);
+int clrrt_comm_init(clrrt_ctx* ctx, const void* id, int bytes, int rank, int world);
+int clrrt_comm_attach(clrrt_ctx* ctx, void* nccl_comm, int rank, int world);
+int clrrt_comm_info(const clrrt_ctx* ctx, int* rank, int* world);
+int clrrt_counters_get_global(clrrt_ctx* ctx, clrrt_counters* out);
+/* Order-sensitive 128-bit digest (sum and xor of per-node hashes of the 160-byte node records and their indices) of tree
+ * nodes [first, first + count), computed on the device: equal on every rank and for every world size when the trees are
+ * equal — the bench and the multi-rank tests compare it. */
+int clrrt_tree_digest(clrrt_ctx* ctx, int first, int count, uint64_t out2[2]);
+
+/* Lower-level form of the same exchange, for callers that move the records themselves: after a round run with append deferred, the nodes accepted by this rank are
  * exposed as fixed-stride records for an all-gather (NCCL), and the gathered records of all ranks are appended
  * in rank order == global sample order, so every rank ends with the same tree for any world size. */
 #define CLRRT_RECORD_BYTES 160

@@ -15,6 +15,11 @@
 extern "C" {
 #endif
 
+/* Error convention: every call returns CLRRT_OK / a count, or a negative clrrt_status; nothing is thrown across the
+ * boundary and nothing is printed.  clrrt_host_last_error() is the text of the last failure on the calling thread (the
+ * reference itself has no error channel: failures are flags and log lines, rrt/src/motionplanner.cpp:56-58). */
+const char* clrrt_host_last_error(void);
+
 /* One MotionPlanner::planMotion query from an empty tree (rrt/src/motionplanner.cpp:8-77, commit_path = false).
  * max_iterations >= 0 replaces Timer(200) by a fixed number of expandTree calls (deterministic); otherwise budget_ms
  * of wall clock.  seed: srand(seed) before the query (the reference never seeds rand(): 1 reproduces it).

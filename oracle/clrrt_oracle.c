@@ -355,6 +355,7 @@ typedef struct {
   double ref_bx, ref_by, ref_vback, trace, idwp0;
 } orc_sim;
 
+static int gen_profile_flag = 1; /* the constructor's genProfile argument; every call site upstream passes true */
 /* Simulation ctor :36-47 + propagate :55-143.  traj (optional) receives stateArray, (n_steps+1) x 10. */
 static void simulate(const double* state0, orc_ref* ref, int GoalBiased, double Vstart, orc_sim* out, double* traj,
                      int traj_cap) {
@@ -368,7 +369,7 @@ static void simulate(const double* state0, orc_ref* ref, int GoalBiased, double 
   updateWaypoint(&c, ref, x);
   x[7] = c.IDwp; /* :41 */
   out->idwp0 = c.IDwp;
-  generateVelocityProfile(ref, Vstart, vmax, goalPose, GoalBiased); /* :43 */
+  if (gen_profile_flag) generateVelocityProfile(ref, Vstart, vmax, goalPose, GoalBiased); /* :42-45, genProfile */
   const int N = ref->N;
   out->N = N; out->ref_bx = ref->x[N - 1]; out->ref_by = ref->y[N - 1]; out->ref_vback = ref->v[N - 1];
   if (traj && traj_cap > 0) memcpy(traj, x, sizeof x);
@@ -854,6 +855,32 @@ double orc_obb_dist(const double* a5, const double* b5) {
   return getOBBdist(a, b);
 }
 double orc_obs_distance(const double* x10) { return obsDistance3(x10); }
+/* checkObsDistance for n poses (x, y, theta, t): out[i] = the distance the hook at simulation.cpp:83 sees */
+void orc_obs_distance_batch(const double* pose4, int n, double* out) {
+  for (int i = 0; i < n; i++) {
+    double x[10] = {pose4[4 * i], pose4[4 * i + 1], pose4[4 * i + 2], 0, 0, 0, pose4[4 * i + 3], 0, 0, 0};
+    out[i] = checkObsDistance(x);
+  }
+}
+/* Simulation::Simulation(RRT, state, ref, veh, GoalBiased, genProfile, Vstart) on a caller-supplied reference
+ * (simulation.h:18-19): rx, ry of n points, rv filled when genProfile (else read).  out: 24 doubles (sim_to_out);
+ * traj optional, cap x 10.  Returns the number of stateArray rows. */
+int orc_simulate(const double* state10, const double* rx, const double* ry, double* rv, int n, int dir, int gb, int genProfile,
+                 double Vstart, double* out, double* traj, int cap) {
+  orc_ref ref;
+  ref.N = n; ref.dir = dir;
+  ref.x = malloc(sizeof(double) * (size_t)n); ref.y = malloc(sizeof(double) * (size_t)n); ref.v = NULL;
+  memcpy(ref.x, rx, sizeof(double) * (size_t)n); memcpy(ref.y, ry, sizeof(double) * (size_t)n);
+  if (!genProfile) { ref.v = malloc(sizeof(double) * (size_t)n); memcpy(ref.v, rv, sizeof(double) * (size_t)n); }
+  orc_sim sim;
+  gen_profile_flag = genProfile;
+  simulate(state10, &ref, gb, Vstart, &sim, traj, cap);
+  gen_profile_flag = 1;
+  sim_to_out(out, &sim);
+  memcpy(rv, ref.v, sizeof(double) * (size_t)n);
+  ref_free(&ref);
+  return sim.n_steps + 1;
+}
 void orc_draw_samples(int K, double* sample_xy, unsigned char* heuristic, double* r_out) {
   for (int j = 0; j < K; j++) {
     sampleAroundVehicle(goalPose, &sample_xy[2 * j], &sample_xy[2 * j + 1]);

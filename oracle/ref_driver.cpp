@@ -388,6 +388,28 @@ double ref_obs_distance(const double* x10) {
   vector<double> x(x10, x10 + 10);
   return checkObsDistance(x, g_obstacles, g_carState);
 }
+void ref_obs_distance_batch(const double* pose4, int n, double* out) {
+  for (int i = 0; i < n; i++) {
+    vector<double> x = {pose4[4 * i], pose4[4 * i + 1], pose4[4 * i + 2], 0, 0, 0, pose4[4 * i + 3], 0, 0, 0};
+    out[i] = checkObsDistance(x);  // the hook at rrt/src/simulation.cpp:83 (stub without obstacles)
+  }
+}
+// Simulation::Simulation(RRT, state, ref, veh, GoalBiased, genProfile, Vstart) (rrt/include/rrt/simulation.h:18-19) on a
+// caller-supplied reference; rv is filled when genProfile (the constructor mutates the caller's MyReference).
+int ref_simulate(const double* state10, const double* rx, const double* ry, double* rv, int n, int dir, int gb, int genProfile,
+                 double Vstart, double* out, double* traj, int cap) {
+  const int c0 = fail_collision, a0 = fail_acclimit, i0 = fail_iterlimit;
+  MyReference ref;
+  ref.x.assign(rx, rx + n); ref.y.assign(ry, ry + n); ref.dir = dir;
+  if (!genProfile) ref.v.assign(rv, rv + n);
+  vector<double> st(state10, state10 + 10);
+  Simulation sim(*g_rrt, st, ref, g_veh, gb != 0, genProfile != 0, Vstart);
+  fill_out(out, sim, ref, c0, a0, i0);
+  for (int i = 0; i < n && i < (int)ref.v.size(); i++) rv[i] = ref.v[i];
+  const int rows = std::min<int>(cap, (int)sim.stateArray.size());
+  if (traj) for (int i = 0; i < rows; i++) for (int k = 0; k < 10; k++) traj[10 * i + k] = sim.stateArray[i][k];
+  return (int)sim.stateArray.size();
+}
 // sampleAroundVehicle + the heuristic draw, in the order of rrt/src/rrtplanner.cpp:133-143.
 void ref_draw_samples(int K, double* sample_xy, unsigned char* heuristic, double* r_out) {
   for (int j = 0; j < K; j++) {

@@ -224,6 +224,27 @@ class CpuPlanner:
         x = np.ascontiguousarray(x10, dtype=np.float64)
         return self._f("obs_distance")(_ptr(x))
 
+    def obs_distance_batch(self, poses_xytht):
+        p = np.ascontiguousarray(poses_xytht, dtype=np.float64).reshape(-1, 4)
+        out = np.zeros(len(p))
+        self._f("obs_distance_batch")(_ptr(p), C.c_int(len(p)), _ptr(out))
+        return out
+
+    def simulate(self, state10, ref_x, ref_y, ref_v=None, gb=0, gen_profile=1, vstart=0.0, ref_dir=1, cap=512):
+        """Simulation::Simulation(RRT, state, ref, veh, GoalBiased, genProfile, Vstart) on a caller-supplied reference.
+        Returns (24-column record, ref_v, stateArray)."""
+        st = np.ascontiguousarray(state10, dtype=np.float64)
+        x = np.ascontiguousarray(ref_x, dtype=np.float64)
+        y = np.ascontiguousarray(ref_y, dtype=np.float64)
+        v = np.zeros(len(x)) if ref_v is None else np.array(ref_v, dtype=np.float64)
+        out = np.zeros(OUT_STRIDE)
+        traj = np.zeros((cap, 10))
+        f = self._f("simulate")
+        f.argtypes = [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_double, C.c_void_p, C.c_void_p, C.c_int]
+        n = f(_ptr(st), _ptr(x), _ptr(y), _ptr(v), len(x), int(ref_dir), int(gb), int(gen_profile), float(vstart), _ptr(out),
+              _ptr(traj), cap)
+        return out, v, traj[:min(n, cap)]
+
     def best_path(self, cap=4096):
         ids = np.zeros(cap, dtype=np.int32)
         n = self._f("best_path")(_ptr(ids), C.c_int(cap))

@@ -39,7 +39,7 @@ def test_struct_layouts_match_header():
     assert clrrt.OBSTACLE_DTYPE.itemsize == 56
     assert C.sizeof(clrrt.Vehicle) == 14 * 8
     assert C.sizeof(clrrt.Params) == 14 * 8 + 11 * 8 + 5 * 8 + 4 * 8 + 8 + 3 * 8 + 8 + 8
-    assert C.sizeof(clrrt.RoundStats) == 6 * 4 + 8 + 4 * 4
+    assert C.sizeof(clrrt.RoundStats) == 6 * 4 + 8 + 4 * 4 + 4 + 4
     assert clrrt.RECORD_BYTES == 160
 
 

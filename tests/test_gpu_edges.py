@@ -141,13 +141,20 @@ def test_non_finite_samples_and_full_tree(clrrt, planner):
     assert st.nodes_added > 0 and planner.tree_size() == 1 + st.nodes_added
     nodes = planner.tree_download()
     assert np.isfinite(nodes["state"][:, :7]).all()
-    # a tree that cannot take the round's nodes: error code, nothing half-appended
+    # a tree that cannot take all of the round's nodes: CLRRT_ERR_CAPACITY, and the prefix that fits IS appended — records
+    # are in sample order, so these are the nodes the sequential reference would have added first (a query that fills
+    # its tree keeps what it grew)
+    s, h = clrrt.draw_samples(GOAL, 1024, seed=5)
+    planner.tree_reset(clrrt.root_node(CAR))
+    planner.expand_round(s, h)
+    full = planner.tree_download()
+    assert len(full) > 64
     small = clrrt.Planner(device=0, tree_capacity=64, max_round=1 << 10)
     small.set_query(CAR, GOAL, 5.0)
     small.set_obstacles(scene_c1_boxes())
     small.tree_reset(clrrt.root_node(CAR))
-    s, h = clrrt.draw_samples(GOAL, 1024, seed=5)
-    with pytest.raises(clrrt.ClrrtError):
+    with pytest.raises(clrrt.ClrrtError, match="capacity"):
         small.expand_round(s, h)
-    assert small.tree_size() == 1
+    assert small.tree_size() == 64
+    assert small.tree_download().tobytes() == full[:64].tobytes()
     small.close()
