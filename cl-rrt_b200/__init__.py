@@ -40,6 +40,12 @@ class RoundStats(C.Structure):
                 ("ms_prepare", C.c_float), ("ms_append", C.c_float), ("ms_exchange", C.c_float), ("nodes_local", C.c_int32)]
 
 
+class SeqStats(C.Structure):
+    _fields_ = [("iterations", C.c_int64), ("sim_steps", C.c_int64), ("rollouts", C.c_int64), ("windows", C.c_int32),
+                ("speculated", C.c_int32), ("nodes_added", C.c_int32), ("tree_size", C.c_int32),
+                ("exact_fallbacks", C.c_int32), ("ms_total", C.c_float)]
+
+
 class Counters(C.Structure):
     _fields_ = [("fail_collision", C.c_int64), ("fail_acclimit", C.c_int64), ("fail_iterlimit", C.c_int64),
                 ("sim_count", C.c_int64), ("rollouts", C.c_int64)]
@@ -102,6 +108,7 @@ def load_library():
     lib.clrrt_set_nearest_mode.argtypes = [vp, ip]
     lib.clrrt_tree_download_range.argtypes = [vp, ip, ip, vp]
     lib.clrrt_draw_samples.argtypes = [vp, ip, vp, vp]
+    lib.clrrt_expand_sequential.argtypes = [vp, vp, vp, ip, ip, C.POINTER(SeqStats)]
     lib.clrrt_comm_unique_id.argtypes = [vp, ip]
     lib.clrrt_comm_init.argtypes = [vp, vp, ip, ip, ip]
     lib.clrrt_comm_attach.argtypes = [vp, vp, ip, ip]
@@ -373,6 +380,15 @@ class Planner:
         h = np.ascontiguousarray(heuristic, dtype=np.uint8)
         st = RoundStats()
         self._ck(self.lib.clrrt_expand_round(self.h, s.ctypes.data, h.ctypes.data, len(s), C.byref(st)))
+        return st
+
+    def expand_sequential(self, samples, heuristic, window=0):
+        """len(samples) consecutive expandTree calls (the reference's sequential algorithm), executed as speculative
+        windows on the device (clrrt_expand_sequential).  window: samples in flight (0 = adaptive)."""
+        s = np.ascontiguousarray(samples, dtype=np.float64).reshape(-1, 2)
+        h = np.ascontiguousarray(heuristic, dtype=np.uint8)
+        st = SeqStats()
+        self._ck(self.lib.clrrt_expand_sequential(self.h, s.ctypes.data, h.ctypes.data, len(s), int(window), C.byref(st)))
         return st
 
     def expand_round_dev(self, d_samples_ptr, d_heur_ptr, K):

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -16,6 +17,7 @@
 #include "simulate.cuh"
 #include "tree.cuh"
 #include "exchange.cuh"
+#include "sequential.cuh"
 
 namespace {
 
@@ -349,10 +351,10 @@ int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_r
   ctx->init_stride = ((K * CLRRT_SORT_LIMIT + (size_t)ctx->num_sms * ROLLOUT_MAX_THREADS_PER_SM) + 31) & ~(size_t)31;
   ok &= mal(&ctx->d_init, ctx->init_stride * LANE_INIT_BYTES_PER_RECORD);
   ok &= mal((void**)&ctx->d_slot, K * sizeof(int32_t));
-  ok &= mal((void**)&ctx->d_res_code, K * CLRRT_SORT_LIMIT);
-  ok &= mal((void**)&ctx->d_res_steps, K * CLRRT_SORT_LIMIT * sizeof(uint16_t));
+  ok &= mal((void**)&ctx->d_res_code, K * (CLRRT_SORT_LIMIT + 1));  // + the goal-biased rollout of every sample
+  ok &= mal((void**)&ctx->d_res_steps, K * (CLRRT_SORT_LIMIT + 1) * sizeof(uint16_t));
   ok &= mal((void**)&ctx->d_ref_end, K * CLRRT_SORT_LIMIT * 2 * sizeof(double));
-  ok &= mal((void**)&ctx->d_ints, 16 * sizeof(int32_t));
+  ok &= mal((void**)&ctx->d_ints, 128 * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_block_sums, ((K + SCAN_THREADS - 1) / SCAN_THREADS + 1) * sizeof(int32_t));
   ok &= mal((void**)&ctx->d_records, 2 * K * sizeof(NodeRecord));
   ok &= mal((void**)&ctx->d_counters, 32 * sizeof(unsigned long long));
@@ -365,7 +367,7 @@ int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_r
   ok &= cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(unsigned long long)) == cudaSuccess;
   if (!ok) { ctx->err = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()); return fail(CLRRT_ERR_CUDA); }
   cudaMemsetAsync(ctx->d_counters, 0, 32 * sizeof(unsigned long long), ctx->stream);
-  cudaMemsetAsync(ctx->d_ints, 0, 16 * sizeof(int32_t), ctx->stream);
+  cudaMemsetAsync(ctx->d_ints, 0, 128 * sizeof(int32_t), ctx->stream);
   for (auto& e : ctx->ev) cudaEventCreate(&e);
   fill_dev_params(ctx);
   if ((rc = configure_launch(ctx)) != CLRRT_OK) return fail(rc);
@@ -740,9 +742,9 @@ static int nearest_reference_ties(clrrt_ctx* ctx, const double* d_samples, const
 }
 
 static int nearest_dev(clrrt_ctx* ctx, const double* d_samples, const uint8_t* d_heur, int K, int32_t* d_cand,
-                       float* d_key, int32_t* d_count) {
+                       float* d_key, int32_t* d_count, bool window = false) {
   const bool sorted = ctx->nn_mode == 1 || (ctx->nn_mode == 0 && (double)K * (double)ctx->n_tree >= NN_SORT_MIN_PAIRS);
-  const bool ref_ties = K == 1 && ctx->tie_mode == 1;
+  const bool ref_ties = K == 1 && ctx->tie_mode == 1 && !window;  // windows flag ties themselves (tie_window_kernel)
   if (ref_ties && !d_key) d_key = ctx->d_key;
   if (!sorted) {
     NearestArgs a;
@@ -990,18 +992,16 @@ static int append_local(clrrt_ctx* ctx, const NodeRecord* d_rec, int n) {
   return CLRRT_OK;
 }
 
-int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint8_t* d_heuristic, int K,
-                           clrrt_round_stats* stats) {
-  if (!ctx || !d_sample_xy || !d_heuristic || K < 1) return CLRRT_ERR_ARG;
-  if (!ctx->have_tree) return CLRRT_ERR_STATE;
-  if (K > ctx->max_round) return CLRRT_ERR_CAPACITY;
-  CK(cudaSetDevice(ctx->device));
-  int rc = ensure_params(ctx);
-  if (rc) return rc;
+// Candidate search, rollouts of all candidates with first-success semantics and goal-biased continuations, winner per
+// sample: everything of a round up to the staging SoA.  `window`: a speculative window of the sequential mode
+// (sequential.cuh) — the candidate keys are kept, the goal-biased rollouts' results are recorded per sample and nothing
+// is added to the failure counters (seq_commit_kernel counts the committed samples only).
+static int round_core(clrrt_ctx* ctx, const double* d_sample_xy, const uint8_t* d_heuristic, int K, bool window) {
+  int rc;
   cudaStream_t st = ctx->stream;
   CK(cudaEventRecord(ctx->ev[0], st));
   // 1. candidate parents
-  if ((rc = nearest_dev(ctx, d_sample_xy, d_heuristic, K, ctx->d_cand, nullptr, ctx->d_count))) return rc;
+  if ((rc = nearest_dev(ctx, d_sample_xy, d_heuristic, K, ctx->d_cand, window ? ctx->d_key : nullptr, ctx->d_count, window))) return rc;
   CK(cudaEventRecord(ctx->ev[1], st));
   // 2. rollouts of all candidates, rank-major (longest references first within a rank), with early skip: equivalent to
   //    trying them in order until the first success; the goal-biased rollout of a sample's winner continues on the lane
@@ -1011,6 +1011,7 @@ int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint
   CK(cudaMemsetAsync(ctx->d_done, 0, (size_t)K * sizeof(uint32_t), st));
   CK(cudaMemsetAsync(ctx->d_valid + K, 0, (size_t)K * sizeof(int32_t), st));
   CK(cudaMemsetAsync(ctx->d_hist, 0, 1024 * sizeof(int32_t), st));
+  if (window) CK(cudaMemsetAsync(ctx->d_res_code + n_pairs, 0, (size_t)K, st));
   CK(cudaMemcpyAsync(ctx->h_counters + 8, ctx->d_counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   ref_end_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(K, CLRRT_SORT_LIMIT, ctx->d_cand, CLRRT_SORT_LIMIT, ctx->d_count, d_sample_xy,
                                                        n_pairs, ctx->tree, ctx->d_ref_end, ctx->d_bucket, ctx->d_hist);
@@ -1023,8 +1024,9 @@ int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint
   job.head = ctx->d_ints + 0; job.cand = ctx->d_cand; job.count = ctx->d_count; job.order = ctx->d_order;
   job.cand_stride = CLRRT_SORT_LIMIT; job.sample_xy = d_sample_xy; job.parents = ctx->tree; job.ref_end = ctx->d_ref_end;
   job.sample_word = ctx->d_done; job.res_code = ctx->d_res_code; job.res_steps = ctx->d_res_steps;
+  job.gb_results = window ? 1 : 0;
   job.out_nodes = ctx->stage; job.out_valid = ctx->d_valid;
-  job.counters = ctx->d_counters; job.refill_min = ctx->refill_min; job.phase_clk = ctx->d_counters + 8;
+  job.counters = window ? nullptr : ctx->d_counters; job.refill_min = ctx->refill_min; job.phase_clk = ctx->d_counters + 8;
   job.init = ctx->d_init; job.init_stride = ctx->init_stride;
 #ifdef CLRRT_PHASE_CLOCKS
   job.timeline = ctx->d_timeline;
@@ -1039,9 +1041,22 @@ int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint
   SelectArgs sa;
   sa.K = K; sa.n_ranks = CLRRT_SORT_LIMIT; sa.count = ctx->d_count; sa.sample_word = ctx->d_done;
   sa.res_code = ctx->d_res_code; sa.res_steps = ctx->d_res_steps; sa.valid = ctx->d_valid;
-  sa.slot = ctx->d_slot; sa.counters = ctx->d_counters;
+  sa.slot = ctx->d_slot; sa.counters = window ? nullptr : ctx->d_counters;
   select_kernel<<<(K + 255) / 256, 256, 0, st>>>(sa);
   CK(cudaGetLastError());
+  return CLRRT_OK;
+}
+
+int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint8_t* d_heuristic, int K,
+                           clrrt_round_stats* stats) {
+  if (!ctx || !d_sample_xy || !d_heuristic || K < 1) return CLRRT_ERR_ARG;
+  if (!ctx->have_tree) return CLRRT_ERR_STATE;
+  if (K > ctx->max_round) return CLRRT_ERR_CAPACITY;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_params(ctx);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  if ((rc = round_core(ctx, d_sample_xy, d_heuristic, K, false))) return rc;
   CK(cudaEventRecord(ctx->ev[3], st));
   // 4. compaction in sample order -> records -> append
   const int nblocks = (K + SCAN_THREADS - 1) / SCAN_THREADS;
@@ -1106,6 +1121,83 @@ int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint
     cudaEventElapsedTime(&stats->ms_exchange, ctx->ev[6], ctx->ev[4]);
   }
   return rc_append;
+}
+
+// == n consecutive calls of expandTree (rrt/src/rrtplanner.cpp:123-174), each seeing the nodes of the calls before it —
+// the reference's own sequential algorithm — executed as speculative windows (sequential.cuh)
+int clrrt_expand_sequential(clrrt_ctx* ctx, const double* sample_xy, const uint8_t* heuristic, int n, int window,
+                            clrrt_seq_stats* stats) {
+  if (!ctx || !sample_xy || !heuristic || n < 1 || window < 0) return CLRRT_ERR_ARG;
+  if (!ctx->have_tree) return CLRRT_ERR_STATE;
+  if (ctx->world > 1) { ctx->err = "clrrt_expand_sequential does not shard (replicas only)"; return CLRRT_ERR_STATE; }
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_params(ctx);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  const int wmax = std::min(std::min(window > 0 ? window : 16, SEQ_MAX_WINDOW), ctx->max_round);
+  clrrt_seq_stats acc;
+  memset(&acc, 0, sizeof acc);
+  const auto t_begin = std::chrono::steady_clock::now();
+  CK(cudaMemcpyAsync(ctx->h_counters + 8, ctx->d_counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const unsigned long long steps0 = ctx->h_counters[11], roll0 = ctx->h_counters[12];
+  int pos = 0, w_next = window > 0 ? wmax : std::min(8, wmax);
+  int rc_out = CLRRT_OK;
+  while (pos < n) {
+    // samples are uploaded in chunks of at most max_round
+    const int chunk0 = pos, chunk = std::min(n - pos, ctx->max_round);
+    CK(cudaMemcpyAsync(ctx->d_samples, sample_xy + 2 * (size_t)chunk0, (size_t)chunk * 16, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_heur, heuristic + chunk0, (size_t)chunk, cudaMemcpyHostToDevice, st));
+    while (pos < chunk0 + chunk) {
+      const int w = std::min(w_next, chunk0 + chunk - pos);
+      const double* d_s = ctx->d_samples + 2 * (size_t)(pos - chunk0);
+      const uint8_t* d_h = ctx->d_heur + (pos - chunk0);
+      if ((rc = round_core(ctx, d_s, d_h, w, true))) return rc;
+      CK(cudaMemsetAsync(ctx->d_ints + 8, 0, (3 + SEQ_MAX_WINDOW) * sizeof(int32_t), st));
+      int32_t* d_tie = ctx->d_ints + 11;
+      if (ctx->tie_mode == 1) {
+        TieWindowArgs t;
+        t.tree = ctx->tree; t.n_nodes = ctx->n_tree; t.sample_xy = d_s; t.heuristic = d_h; t.cand = ctx->d_cand; t.key = ctx->d_key;
+        t.count = ctx->d_count; t.feas_len = ctx->dprm.feas_len; t.flag = d_tie;
+        tie_window_kernel<<<dim3((ctx->n_tree + 127) / 128, w), 128, 0, st>>>(t);
+        CK(cudaGetLastError());
+      }
+      SeqCommitArgs c;
+      c.tree = ctx->tree; c.stage = ctx->stage; c.n_tree = ctx->n_tree; c.capacity = ctx->cap; c.w = w; c.n_ranks = CLRRT_SORT_LIMIT;
+      c.sample_xy = d_s; c.heuristic = d_h; c.key = ctx->d_key; c.count = ctx->d_count; c.sample_word = ctx->d_done;
+      c.valid = ctx->d_valid; c.slot = ctx->d_slot; c.res_code = ctx->d_res_code; c.res_steps = ctx->d_res_steps; c.tie_flag = d_tie;
+      c.feas_len = ctx->dprm.feas_len; c.counters = ctx->d_counters; c.out = ctx->d_ints + 8;
+      seq_commit_kernel<<<1, SEQ_THREADS, 0, st>>>(c);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(ctx->h_ints + 8, ctx->d_ints + 8, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      const int committed = ctx->h_ints[8], appended = ctx->h_ints[9], stop = ctx->h_ints[10];
+      ctx->n_tree += appended;
+      acc.windows++; acc.nodes_added += appended; acc.speculated += w;
+      pos += committed;
+      if (stop == 3) { ctx->err = "tree capacity exceeded"; rc_out = CLRRT_ERR_CAPACITY; pos = n; break; }
+      if (stop == 1 && committed == 0) {
+        // the first sample's own candidate list holds equal keys: the K = 1 path repeats the reference's std::sort
+        clrrt_round_stats st1;
+        rc = clrrt_expand_round_dev(ctx, d_s, d_h, 1, &st1);
+        if (rc == CLRRT_ERR_CAPACITY) { rc_out = rc; pos = n; break; }
+        if (rc) return rc;
+        acc.exact_fallbacks++; acc.nodes_added += st1.nodes_added;
+        pos += 1;
+      }
+      // window size: follow the length of the committed runs (a conflict wastes the rest of the window)
+      if (window == 0) w_next = std::max(4, std::min(wmax, 2 * std::max(committed, 1) + 2));
+    }
+  }
+  CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  acc.iterations = n;
+  acc.sim_steps = (int64_t)(ctx->h_counters[3] - steps0);
+  acc.rollouts = (int64_t)(ctx->h_counters[4] - roll0);
+  acc.tree_size = ctx->n_tree;
+  acc.ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+  if (stats) *stats = acc;
+  return rc_out;
 }
 
 int clrrt_expand_round(clrrt_ctx* ctx, const double* sample_xy, const uint8_t* heuristic, int K,

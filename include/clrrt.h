@@ -197,6 +197,24 @@ int clrrt_collide_batch(clrrt_ctx* ctx, const double* pose_xytht, int n, int32_t
  * sample order.  K == 1 is the reference's sequential algorithm exactly. */
 int clrrt_expand_round(clrrt_ctx* ctx, const double* sample_xy, const uint8_t* heuristic, int K,
                        clrrt_round_stats* stats);
+/* == n CONSECUTIVE calls of expandTree (the loop of rrt/src/motionplanner.cpp:39-43): sample i sees the nodes appended by
+ * samples 0..i-1 — the reference's sequential algorithm, the only formulation that equals it per query (K > 1 rounds are
+ * a different algorithm, see clrrt_expand_round).  The result (tree, parents, counters) is exactly that of n calls of
+ * clrrt_expand_round with K = 1, including the reference's order of equal keys (clrrt_set_tie_mode), but the device works
+ * on a WINDOW of upcoming samples at a time: their candidate searches and rollouts run speculatively against the current
+ * tree and are committed in order for as long as no node appended earlier in the window could have changed a sample's
+ * candidate list up to its winner (cl-rrt_b200/csrc/sequential.cuh); the first sample that fails the test starts the next
+ * window.  window: samples in flight, 1..64 (0 = adaptive).  Does not shard across ranks. */
+typedef struct clrrt_seq_stats {
+  int64_t iterations, sim_steps, rollouts;
+  int32_t windows;          /* speculative windows run */
+  int32_t speculated;       /* samples speculated in total (>= iterations; the excess was run twice) */
+  int32_t nodes_added, tree_size;
+  int32_t exact_fallbacks;  /* samples whose candidate list depended on std::sort's order of equal keys (host route) */
+  float ms_total;           /* wall clock of the call */
+} clrrt_seq_stats;
+int clrrt_expand_sequential(clrrt_ctx* ctx, const double* sample_xy, const uint8_t* heuristic, int n, int window,
+                            clrrt_seq_stats* stats);
 /* Same, samples already resident in device memory (bench: inputs in HBM before the timed region). */
 int clrrt_expand_round_dev(clrrt_ctx* ctx, const double* d_sample_xy, const uint8_t* d_heuristic, int K,
                            clrrt_round_stats* stats);
