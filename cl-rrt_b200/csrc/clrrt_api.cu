@@ -1284,6 +1284,19 @@ int clrrt_debug_phase_clocks(clrrt_ctx* ctx, unsigned long long out[16], int res
   return CLRRT_OK;
 }
 
+// self-check of the branch-free division (rollout.cuh, div_nb) against the operator: see div_check_kernel
+int clrrt_debug_div_check(clrrt_ctx* ctx, unsigned long long seed, int pairs_per_thread, unsigned long long out[3]) {
+  if (!ctx || !out || pairs_per_thread < 1) return CLRRT_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  unsigned long long* d = ctx->d_counters + 24;
+  CK(cudaMemsetAsync(d, 0, 3 * sizeof(unsigned long long), ctx->stream));
+  div_check_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(seed, pairs_per_thread, d);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, d, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return CLRRT_OK;
+}
+
 // diagnostic builds (-DCLRRT_PHASE_CLOCKS) only: start/end/steps of every rollout of the last round, 3 words per staging slot
 int clrrt_debug_timeline(clrrt_ctx* ctx, unsigned long long* out, int K) {
   if (!ctx || !out || K < 1 || K > ctx->max_round) return CLRRT_ERR_ARG;

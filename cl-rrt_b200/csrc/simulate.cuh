@@ -213,3 +213,40 @@ collide_batch_kernel(const double* __restrict__ pose4, int n, int32_t* __restric
     if (dobs) dobs[i] = d;
   }
 }
+
+// div_nb against the division operator on n operand pairs per class (tests/test_gpu_rollout.py): class 0 = the magnitudes
+// the rollout divides (1e-6 .. 1e4, both signs), 1 = random bit patterns (every exponent, NaN, Inf, subnormals), 2 = dividend
+// or divisor at the edges of the fast path's range.  out[0] = pairs whose fast-path result was accepted, out[1] = accepted
+// results that differ from a / b (must be 0), out[2] = pairs sent to the operator.
+__device__ __forceinline__ unsigned long long splitmix(unsigned long long& s) {
+  unsigned long long z = (s += 0x9e3779b97f4a7c15ull);
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256) div_check_kernel(unsigned long long seed, int per_thread, unsigned long long* out) {
+  unsigned long long s = seed + 0x1234567ull * (blockIdx.x * blockDim.x + threadIdx.x);
+  unsigned long long acc = 0, diff = 0, slow = 0;
+  for (int it = 0; it < per_thread; it++) {
+    const int cls = it % 3;
+    double a, b;
+    const unsigned long long r0 = splitmix(s), r1 = splitmix(s);
+    if (cls == 0) {
+      const double ea = -6.0 + 10.0 * (double)(r0 >> 40) / 16777216.0, eb = -6.0 + 10.0 * (double)(r1 >> 40) / 16777216.0;
+      a = exp10(ea) * (1.0 + (double)(r0 & 0xffffff) / 16777216.0) * ((r0 >> 30) & 1 ? -1.0 : 1.0);
+      b = exp10(eb) * (1.0 + (double)(r1 & 0xffffff) / 16777216.0) * ((r1 >> 30) & 1 ? -1.0 : 1.0);
+    } else if (cls == 1) {
+      a = __longlong_as_double((long long)r0); b = __longlong_as_double((long long)r1);
+    } else {
+      const int ka = (int)(r0 % 7), kb = (int)(r1 % 5);
+      const double edge[7] = {0.0, 1e-300, 1e-38, 6.6e-37, 1e300, 1.0, 3.0};
+      const double edgb[5] = {1e-300, 1e300, 1.0, 7.0, 1e-38};
+      a = edge[ka] * (1.0 + (double)(r0 >> 44) / 1048576.0); b = edgb[kb] * (1.0 + (double)(r1 >> 44) / 1048576.0);
+    }
+    bool bad = false;
+    const double q = div_nb(a, b, bad), w = a / b;
+    if (bad) slow++;
+    else { acc++; if (__double_as_longlong(q) != __double_as_longlong(w)) diff++; }
+  }
+  atomicAdd(&out[0], acc); atomicAdd(&out[1], diff); atomicAdd(&out[2], slow);
+}

@@ -215,6 +215,19 @@ clrrt_round_stats expandTree(Vehicle&, MyRRT& RRT, int K) {
   return st;
 }
 
+// n consecutive expandTree calls (the loop body of rrt/src/motionplanner.cpp:39-43 n times): same draws, same tree, same
+// counters as n calls of expandTree(veh, RRT, 1), with several samples in flight on the device (clrrt_expand_sequential)
+clrrt_seq_stats expandTreeSequential(Vehicle&, MyRRT& RRT, int n, int window) {
+  std::vector<double> s(2 * (size_t)n);
+  std::vector<uint8_t> h((size_t)n);
+  clrrt_draw_samples(RRT.goalPose.data(), n, s.data(), h.data());  // 3 rand() per iteration, in the reference's order
+  clrrt_seq_stats st;
+  const int rc = clrrt_expand_sequential(RRT.ctx(), s.data(), h.data(), n, window, &st);
+  if (rc == CLRRT_ERR_CAPACITY) { RRT.treeFull = true; return st; }
+  ck(RRT.ctx(), rc, "clrrt_expand_sequential");
+  return st;
+}
+
 namespace {
 // one rollout with trajectory and reference dumps -> stateArray + MyReference
 void rematerialise(const MyRRT& RRT, int parent, const double sxy[2], bool gb, clrrt_rollout& r, StateArray& states,
@@ -239,6 +252,39 @@ Simulation::Simulation(const MyRRT& RRT, int parent, const Point& sample, const 
   clrrt_rollout r;
   const double sxy[2] = {sample.x, sample.y};
   rematerialise(RRT, parent, sxy, GoalBiased, r, stateArray, ref);
+  costE = r.costE; costS = r.costS; goalReached = r.goal_reached != 0; endReached = r.end_reached != 0; failCode = r.fail;
+}
+
+// the reference's own parameter list (rrt/include/rrt/simulation.h:18-19, rrt/src/simulation.cpp:36-47)
+Simulation::Simulation(const MyRRT& RRT, const std::vector<double>& state, MyReference& ref, const Vehicle&, const bool& GoalBiased,
+                       const bool& genProfile, const double& Vstart) {
+  if (state.size() < 6) throw Error("Simulation: state needs at least [x, y, theta, delta, v, a]");
+  if (ref.x.size() < 3 || ref.y.size() != ref.x.size()) throw Error("Simulation: the reference needs at least 3 points (reference.cpp:19)");
+  double st[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (size_t k = 0; k < 10 && k < state.size(); k++) st[k] = state[k];
+  const int N = (int)ref.x.size(), tstride = CLRRT_MAX_STEPS_CAP;
+  std::vector<double> v((size_t)N, 0.0), traj((size_t)tstride * 10);
+  clrrt_rollout r;
+  bool gen = genProfile;
+  if (genProfile && !ref.v.empty()) {
+    // upstream generateVelocityProfile push_backs onto ref.v (reference.cpp:134-146): with a non-empty ref.v the rollout
+    // reads the OLD leading entries.  No call site does this; reproduce it anyway: profile first, then simulate on the
+    // concatenation's first N entries.
+    ck(RRT.ctx(), clrrt_simulate(RRT.ctx(), st, ref.x.data(), ref.y.data(), v.data(), N, ref.dir, GoalBiased ? 1 : 0, 1, Vstart, &r, nullptr, 0),
+       "clrrt_simulate");
+    ref.v.insert(ref.v.end(), v.begin(), v.end());
+    for (int i = 0; i < N; i++) v[(size_t)i] = ref.v[(size_t)i];
+    gen = false;
+  } else if (!genProfile) {
+    if ((int)ref.v.size() < N) throw Error("Simulation: genProfile == false needs ref.v of the reference's length");
+    for (int i = 0; i < N; i++) v[(size_t)i] = ref.v[(size_t)i];
+  }
+  ck(RRT.ctx(), clrrt_simulate(RRT.ctx(), st, ref.x.data(), ref.y.data(), v.data(), N, ref.dir, GoalBiased ? 1 : 0, gen ? 1 : 0, Vstart, &r,
+                               traj.data(), tstride), "clrrt_simulate");
+  if (gen) ref.v.assign(v.begin(), v.end());  // the constructor fills the caller's reference (simulation.cpp:43)
+  stateArray.clear();
+  for (int i = 0; i <= r.n_steps && i < tstride; i++) stateArray.emplace_back(traj.begin() + 10 * i, traj.begin() + 10 * (i + 1));
+  this->ref = ref;
   costE = r.costE; costS = r.costS; goalReached = r.goal_reached != 0; endReached = r.end_reached != 0; failCode = r.fail;
 }
 
@@ -350,6 +396,8 @@ bool MotionPlanner::resetPlanner() {
 }
 MotionPlanner::~MotionPlanner() { delete rrt_; }
 void MotionPlanner::planMotion(MotionRequest req) {
+  auto tic = std::chrono::steady_clock::now();
+  auto lap = [&](int k) { const auto now = std::chrono::steady_clock::now(); lastMs[k] = std::chrono::duration<double, std::milli>(now - tic).count(); tic = now; };
   Vehicle veh; veh.setPrius();                                  // :13
   std::vector<double> worldState = state;                       // :14
   std::vector<double> carPose = worldState;                     // transformStateToLocal, transformations.cpp:143-147
@@ -367,25 +415,43 @@ void MotionPlanner::planMotion(MotionRequest req) {
     rrt_->reconfigure(req.goal, req.vmax, carPose[4], params);
   }
   MyRRT& RRT = *rrt_;
+  lap(0);
   RRT.setObstacles(det);                                        // :24
+  lap(1);
   RRT.carState = carPose;
   if (!params.commit_path) bestNodes.clear();                   // :28-30
   RRT.treeFull = false;
   initializeTree(RRT, veh, bestNodes, carPose);                 // :32
   lastCarried = (int)RRT.carried().size();
   lastInitialTree = RRT.treeSize();
+  lap(2);
   int iter = 0;                                                 // :39-43
   auto t0 = std::chrono::steady_clock::now();
-  for (;; iter++) {
-    if (maxIterations >= 0) { if (iter >= maxIterations) break; }
-    else if (std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() >= budget_ms) break;
-    expandTree(veh, RRT, round);
-    if (RRT.treeFull) { iter++; break; }  // capacity reached: keep what was grown, extract the best path below
+  if (round == 1 && sequentialChunk > 1) {
+    // the reference's sequential loop, `sequentialChunk` iterations per call with several of them in flight on the device;
+    // the timer is polled between calls (upstream: between iterations)
+    for (;;) {
+      int n = sequentialChunk;
+      if (maxIterations >= 0) { n = std::min(n, maxIterations - iter); if (n <= 0) break; }
+      else if (std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() >= budget_ms) break;
+      expandTreeSequential(veh, RRT, n, sequentialWindow);
+      iter += n;
+      if (RRT.treeFull) break;
+    }
+  } else {
+    for (;; iter++) {
+      if (maxIterations >= 0) { if (iter >= maxIterations) break; }
+      else if (std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() >= budget_ms) break;
+      expandTree(veh, RRT, round);
+      if (RRT.treeFull) { iter++; break; }  // capacity reached: keep what was grown, extract the best path below
+    }
   }
   lastIterations = iter;
   lastTreeSize = RRT.treeSize();
+  lap(3);
   clrrt_counters_get(RRT.ctx(), &lastCounters);                 // :45
   bestNodes = extractBestPath(RRT, &lastBestIds);               // :51
+  lap(4);
   lastRematError = 0;
   for (size_t i = 0; i < bestNodes.size(); i++) {
     const Node& n = bestNodes[i];
@@ -400,6 +466,7 @@ void MotionPlanner::planMotion(MotionRequest req) {
   filterMPCmessage(msg);                                        // :70
   lastTrajectory = msg;
   if (msg.x.size() >= 3 && pubMPC) pubMPC(msg);                 // :71-74
+  lap(5);
 }
 
 }  // namespace clrrt
@@ -457,7 +524,52 @@ extern "C" int clrrt_host_plan_motion(const double* car_state6, const double* go
   }
 }
 
+// The facade's Simulation with the reference's parameter list, for bindings/tests: returns stateArray.size(); ref_v is
+// filled when gen_profile (the constructor mutates the caller's MyReference); flags3 = {endReached, goalReached, failCode}
+extern "C" int clrrt_host_simulate(const double* goal4, double vmax, const clrrt_obstacle* obs, int n_obs, int device,
+                                   const double* state, int n_state, const double* ref_x, const double* ref_y, double* ref_v, int n_ref,
+                                   int goal_biased, int gen_profile, double Vstart, double* costs2, int32_t* flags3, double* last_state10) {
+  if (!goal4 || !state || !ref_x || !ref_y || !ref_v || n_ref < 0 || n_state < 0) { g_host_error = "clrrt_host_simulate: null argument"; return CLRRT_ERR_ARG; }
+  try {
+    g_host_error.clear();
+    clrrt::Vehicle veh; veh.setPrius();
+    clrrt::PlannerParams prm;
+    std::vector<double> goal(goal4, goal4 + 4);
+    clrrt::MyRRT RRT(goal, {0}, {}, false, veh, prm, vmax, n_state > 4 ? state[4] : 0.0, device, 64, 64);
+    std::vector<clrrt::Obstacle2D> det((size_t)n_obs);
+    for (int i = 0; i < n_obs; i++) {
+      det[i].obb.center.x = obs[i].cx; det[i].obb.center.y = obs[i].cy; det[i].obb.center.theta = obs[i].theta;
+      det[i].obb.size_x = obs[i].size_x; det[i].obb.size_y = obs[i].size_y;
+      det[i].vel.linear.x = obs[i].vx; det[i].vel.linear.y = obs[i].vy;
+    }
+    RRT.setObstacles(det);
+    clrrt::MyReference ref;
+    ref.x.assign(ref_x, ref_x + n_ref); ref.y.assign(ref_y, ref_y + n_ref);
+    if (!gen_profile) ref.v.assign(ref_v, ref_v + n_ref);
+    clrrt::Simulation sim(RRT, std::vector<double>(state, state + n_state), ref, veh, goal_biased != 0, gen_profile != 0, Vstart);
+    for (int i = 0; i < n_ref && i < (int)ref.v.size(); i++) ref_v[i] = ref.v[(size_t)i];
+    if (costs2) { costs2[0] = sim.costE; costs2[1] = sim.costS; }
+    if (flags3) { flags3[0] = sim.endReached; flags3[1] = sim.goalReached; flags3[2] = sim.failCode; }
+    if (last_state10) for (int k = 0; k < 10; k++) last_state10[k] = sim.stateArray.back()[(size_t)k];
+    return (int)sim.stateArray.size();
+  } catch (const std::exception& e) {
+    return host_fail("clrrt_host_simulate", e);
+  }
+}
+
 // ---- persistent planner handle: consecutive queries (receding-horizon loop, config C5) ----------------------------
+// wall-clock milliseconds of the last query's phases: parameters, obstacles, initial tree, expansion, best path, messages
+extern "C" int clrrt_host_planner_timings(void* h, double* ms6) {
+  if (!h || !ms6) return CLRRT_ERR_ARG;
+  for (int k = 0; k < 6; k++) ms6[k] = static_cast<clrrt::MotionPlanner*>(h)->lastMs[k];
+  return CLRRT_OK;
+}
+extern "C" int clrrt_host_planner_set_sequential(void* h, int chunk, int window) {
+  if (!h || chunk < 1 || window < 0 || window > 64) return CLRRT_ERR_ARG;
+  clrrt::MotionPlanner* mp = static_cast<clrrt::MotionPlanner*>(h);
+  mp->sequentialChunk = chunk; mp->sequentialWindow = window;
+  return CLRRT_OK;
+}
 extern "C" void* clrrt_host_planner_create(int device, int samples_per_round, int commit_path, int tree_capacity) {
   clrrt::MotionPlanner* mp = new clrrt::MotionPlanner();
   mp->device = device;

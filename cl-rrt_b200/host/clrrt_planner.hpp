@@ -125,6 +125,9 @@ class MyRRT {
 // expandTree (rrt/src/rrtplanner.cpp:123-174), K samples per call against one tree snapshot.  K == 1 is the
 // reference's algorithm; samples come from sampleAroundVehicle on the C library's rand(), as upstream.
 clrrt_round_stats expandTree(Vehicle& veh, MyRRT& RRT, int K = 1);
+// n consecutive expandTree calls with K = 1 — same draws, tree and counters — with `window` samples in flight on the device
+// (clrrt_expand_sequential; 0 = adaptive)
+clrrt_seq_stats expandTreeSequential(Vehicle& veh, MyRRT& RRT, int n, int window = 0);
 // extractBestPath (rrt/src/rrtplanner.cpp:318-368) with the trajectories of the returned nodes re-materialised.
 std::vector<Node> extractBestPath(MyRRT& RRT, std::vector<int32_t>* ids_out = nullptr);
 // initializeTree (rrt/src/rrtplanner.cpp:39-95): empty committed path -> single root node; otherwise the previous best
@@ -134,9 +137,7 @@ void initializeTree(MyRRT& RRT, const Vehicle& veh, std::vector<Node>& nodes, st
 // getNodeCost (rrt/src/rrtplanner.cpp:105-119)
 double getNodeCost(const MyRRT& RRT, const Vehicle& veh, const double& parentCost, const Node& node, double sim_dt);
 
-// rrt/include/rrt/simulation.h:7-26.  As upstream, everything happens in the constructor.  The rollout starts at
-// tree node `parent` (the reference passes that node's state and a reference built from it, rrtplanner.cpp:151-152)
-// towards `sample`; GoalBiased selects getGoalReference (rrtplanner.cpp:165-166).
+// rrt/include/rrt/simulation.h:7-26.  As upstream, everything happens in the constructor.
 class Simulation {
  public:
   StateArray stateArray;
@@ -144,6 +145,12 @@ class Simulation {
   bool goalReached = false, endReached = false;
   MyReference ref;  // x, y re-materialised on the host by LinearSpacedVector; v holds ref.v.back() only
   int failCode = 0; // 0 none, 1 collision, 2 lateral acceleration, 3 iteration limit
+  // the reference's own parameter list (rrt/include/rrt/simulation.h:18-19): any start state (6 or 10 entries), a caller-owned
+  // reference of any shape; with genProfile the constructor FILLS ref.v, as upstream (the caller stores that ref in the new
+  // Node, rrt/src/rrtplanner.cpp:156).  veh: the planner's vehicle (the context was created with it).
+  Simulation(const MyRRT& RRT, const std::vector<double>& state, MyReference& ref, const Vehicle& veh, const bool& GoalBiased,
+             const bool& genProfile, const double& Vstart);
+  // shorthand for the rollouts expandTree itself starts: from tree node `parent` towards `sample` (rrtplanner.cpp:151-152, :165-166)
   Simulation(const MyRRT& RRT, int parent, const Point& sample, const Vehicle& veh, const bool& GoalBiased);
   bool isvalid() const { return endReached; }
 };
@@ -160,6 +167,8 @@ struct MotionPlanner {
   PlannerParams params;
   int device = 0;
   int samplesPerRound = 1;        // 1 = the reference's sequential expandTree; >1 = snapshot rounds
+  int sequentialChunk = 16;       // samplesPerRound == 1: iterations per device call (1 = one clrrt_expand_round per iteration)
+  int sequentialWindow = 0;       // samples in flight inside a call (0 = adaptive), see clrrt_expand_sequential
   double budget_ms = 200;         // Timer(200), rrt/src/motionplanner.cpp:39 (wall clock here, CPU time upstream)
   int maxIterations = -1;         // >= 0: deterministic iteration budget instead of the timer (tests)
   // results of the last query
@@ -171,6 +180,7 @@ struct MotionPlanner {
   int lastCarried = 0;                // nodes of the previous best path the tree was initialised with (commit_path)
   int lastInitialTree = 0;            // tree size after initializeTree (1 = root only)
   int treeCapacity = 1 << 18;
+  double lastMs[6] = {0, 0, 0, 0, 0, 0};  // wall clock of the last query: parameters, obstacles, initial tree, expansion, best path, messages
   ~MotionPlanner();
 
   void planMotion(MotionRequest req);                       // rrt/src/motionplanner.cpp:8-77

@@ -260,6 +260,10 @@ int clrrt_set_defer_append(clrrt_ctx* ctx, int defer);
 /* Kernel-tuning aid: per-phase clock totals of the rollout kernels (refill, dynamics, collision, finish, warp steps),
  * non-zero only in builds compiled with -DCLRRT_PHASE_CLOCKS. */
 int clrrt_debug_phase_clocks(clrrt_ctx* ctx, unsigned long long out[16], int reset);
+/* Self-check of the rollout kernel's branch-free double division (csrc/rollout.cuh, div_nb) against the division operator
+ * on pairs_per_thread x (SMs x 2048) operand pairs: out = {fast-path results accepted, accepted results that differ (0),
+ * pairs left to the operator}. */
+int clrrt_debug_div_check(clrrt_ctx* ctx, unsigned long long seed, int pairs_per_thread, unsigned long long out[3]);
 int clrrt_round_records(clrrt_ctx* ctx, void** d_records, int* n_records);
 int clrrt_append_records(clrrt_ctx* ctx, const void* d_records, const int32_t* counts, int world, int stride_records);
 

@@ -29,10 +29,25 @@ int clrrt_host_plan_motion(const double* car_state6, const double* goal4, double
                            int device, int* tree_size, int* iterations, clrrt_counters* counters, double* traj8,
                            int traj_cap, int* traj_len, int32_t* best_ids, int best_cap, int* best_len, double* remat_err);
 
+/* clrrt::Simulation with the reference's own parameter list (rrt/include/rrt/simulation.h:18-19) through the C++ facade:
+ * Prius vehicle, launch-file parameters, goal / vmax / obstacles as given; state has n_state (6 or 10) entries; the
+ * reference path is caller-owned (n_ref >= 3 points) and ref_v is FILLED when gen_profile != 0.  Returns
+ * stateArray.size() (or a negative status); costs2 = {costE, costS}; flags3 = {endReached, goalReached, failCode};
+ * last_state10 = stateArray.back(). */
+int clrrt_host_simulate(const double* goal4, double vmax, const clrrt_obstacle* obs, int n_obs, int device, const double* state,
+                        int n_state, const double* ref_x, const double* ref_y, double* ref_v, int n_ref, int goal_biased,
+                        int gen_profile, double Vstart, double* costs2, int32_t* flags3, double* last_state10);
+
 /* Persistent planner: consecutive queries on one device context with MotionPlanner::bestNodes kept between them
  * (commit_path != 0: the next tree is initialised from the previous best path, rrt/src/rrtplanner.cpp:50-94). */
 void* clrrt_host_planner_create(int device, int samples_per_round, int commit_path, int tree_capacity);
 void clrrt_host_planner_destroy(void* h);
+/* samples_per_round == 1 (the reference's sequential loop): iterations per device call and samples in flight inside a call
+ * (clrrt_expand_sequential).  chunk = 1 issues one clrrt_expand_round per iteration; default chunk 16, window 0 = adaptive.
+ * The tree is the same for every setting. */
+int clrrt_host_planner_set_sequential(void* h, int chunk, int window);
+/* wall-clock milliseconds of the last query by phase: parameters, obstacles, initial tree, expansion, best path, messages */
+int clrrt_host_planner_timings(void* h, double* ms6);
 /* goal4 and obs in the car frame; sizes4 = {initial tree size, final tree size, best path nodes, expandTree calls} */
 int clrrt_host_planner_query(void* h, const double* world_state6, const double* goal4, double vmax, const clrrt_obstacle* obs,
                              int n_obs, int max_iterations, double budget_ms, int32_t* sizes4, double* best_cost,

@@ -4,7 +4,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import clrrt_b200 as clrrt
 import bench
-pl = clrrt.Planner(device=0, tree_capacity=bench.TREE_SNAPSHOT + 2 * bench.K_ROUND + 1024, max_round=bench.K_ROUND)
+prm = clrrt.default_params(); prm.fp32 = 1 if os.environ.get('CLRRT_FP32') else 0
+pl = clrrt.Planner(params=prm, device=0, tree_capacity=bench.TREE_SNAPSHOT + 2 * bench.K_ROUND + 1024, max_round=bench.K_ROUND)
 boxes, smp, heu = bench.build_workload(pl, clrrt, 0, 1)
 n0 = pl.tree_size()
 tag = os.environ.get("CLRRT_LIB", "default")

@@ -61,3 +61,36 @@ def test_plan_motion_rounds_and_time_budget():
     r = plan(scene_c1_boxes(), 4096, -1)  # 200 ms wall-clock budget, as rrt/src/motionplanner.cpp:39
     assert r["iters"] >= 1 and r["tree"] > 1000
     print(f"200 ms query, 4096 samples/round: {r['iters']} rounds, {r['tree']} nodes, {r['counters'].sim_count} sim steps")
+
+
+def test_simulation_with_the_reference_parameter_list():
+    """clrrt::Simulation(RRT, state, ref, veh, GoalBiased, genProfile, Vstart) — the reference's own constructor signature
+    (rrt/include/rrt/simulation.h:18-19): arbitrary 6-entry state, caller-owned curved reference, ref.v filled — equals the
+    oracle's restatement of that constructor bit for bit; a failure reports through clrrt_host_last_error."""
+    from cpulib import CpuPlanner
+    lib = C.CDLL(os.path.join(ROOT, "cl-rrt_b200", "libclrrt_host.so"))
+    lib.clrrt_host_last_error.restype = C.c_char_p
+    vp, ip, dp = C.c_void_p, C.c_int, C.c_double
+    lib.clrrt_host_simulate.argtypes = [vp, dp, vp, ip, ip, vp, ip, vp, vp, vp, ip, ip, ip, dp, vp, vp, vp]
+    goal = np.array([50.0, 0, 0, 0])
+    obs = scene_c1_boxes()
+    orc = CpuPlanner("oracle")
+    orc.set_obstacles(obs)
+    orc.tree_init((0, 0, 0, 0, 2.5, 0), goal, 5.0)
+    s = np.linspace(0, 45, 226)
+    x, y = np.ascontiguousarray(s), np.ascontiguousarray(1.2 * np.sin(s / 7.0))
+    for state, gb, gen in (([0.3, -0.4, 0.1, 0.02, 2.5, 0.3], 0, 1), ([0, 0.2, 0, 0, 1.0, 0], 1, 1), ([0, 0, 0.05, 0, 4.0, 0], 0, 0)):
+        st = np.array(state, float)
+        v = np.zeros(len(x)) if gen else np.full(len(x), 3.5)
+        want, wv, wtraj = orc.simulate(np.concatenate([st, np.zeros(4)]), x, y, None if gen else v.copy(), gb=gb, gen_profile=gen, vstart=2.0)
+        costs, flags, last = np.zeros(2), np.zeros(3, np.int32), np.zeros(10)
+        n = lib.clrrt_host_simulate(goal.ctypes.data, 5.0, obs.ctypes.data, len(obs), 0, st.ctypes.data, 6, x.ctypes.data, y.ctypes.data,
+                                    v.ctypes.data, len(x), gb, gen, 2.0, costs.ctypes.data, flags.ctypes.data, last.ctypes.data)
+        assert n == len(wtraj), lib.clrrt_host_last_error()
+        assert np.array_equal(last, want[:10]) and costs[0] == want[10] and costs[1] == want[11]
+        assert flags.tolist() == [int(want[12]), int(want[13]), int(want[15])]
+        assert np.array_equal(v, wv)
+    # fewer than three reference points: an error code and a message, nothing thrown or printed
+    rc = lib.clrrt_host_simulate(goal.ctypes.data, 5.0, None, 0, 0, st.ctypes.data, 6, x.ctypes.data, y.ctypes.data, v.ctypes.data, 2, 0, 1,
+                                 2.0, None, None, None)
+    assert rc < 0 and b"3 points" in lib.clrrt_host_last_error()

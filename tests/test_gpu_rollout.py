@@ -218,3 +218,20 @@ def test_full_size_properties(clrrt, planner):
     planner.set_grid_cell(1.0)
     planner.set_obstacles(boxes)
     assert a.tobytes() == c.tobytes() and a.tobytes() == d.tobytes()
+
+
+def test_branch_free_division(clrrt):
+    """rollout.cuh's div_nb — the compiler's own fast path of the double division with its range test accumulated instead of
+    branched on — gives the operator's result bit for bit wherever it accepts its own result: 2.7e8 operand pairs over the
+    rollout's magnitudes, random bit patterns (every exponent, NaN, Inf, subnormals) and the edges of the accepted range."""
+    import ctypes as C
+    pl = clrrt.Planner(device=0, tree_capacity=64, max_round=64)
+    lib = clrrt.load_library()
+    lib.clrrt_debug_div_check.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int, C.c_void_p]
+    out = (C.c_ulonglong * 3)()
+    assert lib.clrrt_debug_div_check(pl.h, 12345, 900, out) == 0
+    accepted, differ, slow = out[0], out[1], out[2]
+    assert accepted + slow == 900 * 148 * 8 * 256 or accepted + slow > 1e8
+    assert differ == 0, f"{differ} of {accepted} fast-path quotients differ from a / b"
+    assert accepted > 0.5 * (accepted + slow) and slow > 0
+    pl.close()
