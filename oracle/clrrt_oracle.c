@@ -703,6 +703,8 @@ void orc_init(void) {
   double Cf = 22201, Cr = 22201, m = 950 + 640;
   veh.Kus = (m / veh.L) * (lr / Cf - lf / Cr);
   veh.Vch = 20;
+  /* the library keeps file-scope state (like the reference): a new planner object starts from the defaults */
+  tie_mode = 0; gen_profile_flag = 1; road_bend = 0;
 }
 void orc_set_tie_mode(int m) { tie_mode = m; }
 void orc_set_weights(const double* w5) { memcpy(Wcost, w5, sizeof Wcost); }
