@@ -326,7 +326,7 @@ int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_r
   ok &= mal((void**)&ctx->d_bucket, K * CLRRT_SORT_LIMIT);
   {
     const size_t n8 = ((size_t)tree_capacity + 7) & ~(size_t)7, k8 = (K + 7) & ~(size_t)7;
-    const size_t bytes = n8 * (7 * 8 + 3 * 4 + 4 + 4) + (n8 + k8) * 4 + k8 * 4 + 3 * NN_BINS * 4 + 5 * (n8 / NEAREST_TILE + 8) * 4 + 1024;
+    const size_t bytes = n8 * (7 * 8 + 9 * 4 + 4 + 4) + (n8 + k8) * 4 + k8 * 4 + 3 * NN_BINS * 4 + 13 * (n8 / NEAREST_TILE + 8) * 4 + 2048;
     ok &= mal(&ctx->nn_mem, bytes);
     if (ok) {
       unsigned char* p = reinterpret_cast<unsigned char*>(ctx->nn_mem);
@@ -334,7 +334,7 @@ int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_r
       NNSortArgs& s = ctx->nn;
       double** dd[] = {&s.nx, &s.ny, &s.rbx, &s.rby, &s.dpx, &s.dpy, &s.ang};
       for (auto d : dd) *d = reinterpret_cast<double*>(take(n8 * 8));
-      float** ff[] = {&s.ca, &s.sa, &s.ce};
+      float** ff[] = {&s.ca, &s.sa, &s.ce, &s.fx, &s.fy, &s.frx, &s.fry, &s.fdx, &s.fdy};
       for (auto f : ff) *f = reinterpret_cast<float*>(take(n8 * 4));
       s.node_id = reinterpret_cast<int32_t*>(take(n8 * 4));
       s.sbin = reinterpret_cast<int32_t*>(take(n8 * 4));
@@ -787,7 +787,9 @@ static int nearest_dev(clrrt_ctx* ctx, const double* d_samples, const uint8_t* d
   a.cand = d_cand; a.key = d_key; a.count = d_count; a.feas_len = ctx->dprm.feas_len;
   a.so.n_nodes = ctx->n_tree; a.so.n_tiles = n_tiles; a.so.node_id = s.node_id;
   a.so.nx = s.nx; a.so.ny = s.ny; a.so.rbx = s.rbx; a.so.rby = s.rby; a.so.dpx = s.dpx; a.so.dpy = s.dpy; a.so.ang = s.ang;
-  a.so.ca = s.ca; a.so.sa = s.sa; a.so.ce = s.ce; a.so.tile_ulo = ctx->d_tile_ulo; a.so.tile_uhi = ctx->d_tile_uhi; a.so.tile_vlo = ctx->d_tile_vlo; a.so.tile_vhi = ctx->d_tile_vhi; a.so.tile_ce = ctx->d_tile_ce;
+  a.so.ca = s.ca; a.so.sa = s.sa; a.so.ce = s.ce;
+  a.so.fx = s.fx; a.so.fy = s.fy; a.so.frx = s.frx; a.so.fry = s.fry; a.so.fdx = s.fdx; a.so.fdy = s.fdy;
+  a.so.tile_ulo = ctx->d_tile_ulo; a.so.tile_uhi = ctx->d_tile_uhi; a.so.tile_vlo = ctx->d_tile_vlo; a.so.tile_vhi = ctx->d_tile_vhi; a.so.tile_ce = ctx->d_tile_ce;
   a.so.sample_id = s.sample_id; a.so.cb = s.cb; a.so.sb = s.sb;
   const int blocks = (K + NEAREST_WARPS - 1) / NEAREST_WARPS;
   nearest_sorted_kernel<<<blocks, NEAREST_THREADS, 0, ctx->stream>>>(a);

@@ -36,6 +36,7 @@ struct NearestSorted {
   const int32_t* node_id;   // [n_nodes] original id of the node at a sorted position
   const double *nx, *ny, *rbx, *rby, *dpx, *dpy, *ang;   // sorted copies
   const float *ca, *sa, *ce;
+  const float *fx, *fy, *frx, *fry, *fdx, *fdy;         // float copies of nx, ny, rbx, rby, dpx, dpy: all a tile stages
   const float* tile_ulo;    // [n_tiles] axis interval of every tile of NEAREST_TILE sorted nodes
   const float* tile_uhi;
   const float* tile_vlo;    // [n_tiles] lateral interval (infinite for tiles that span more than one axis slab)
@@ -73,6 +74,7 @@ struct NNSortArgs {
   int32_t* node_id;
   double *nx, *ny, *rbx, *rby, *dpx, *dpy, *ang;
   float *ca, *sa, *ce;
+  float *fx, *fy, *frx, *fry, *fdx, *fdy;
   int32_t* sbin;       // [n_nodes] bin of the node at a sorted position
   int32_t* sample_id;
 };
@@ -134,7 +136,10 @@ __global__ void __launch_bounds__(256) nn_scatter_kernel(const NNSortArgs a) {
     a.node_id[pos] = i;
     const double x = a.tree.x[i], y = a.tree.y[i], rbx = a.tree.rbx[i], rby = a.tree.rby[i];
     a.nx[pos] = x; a.ny[pos] = y; a.rbx[pos] = rbx; a.rby[pos] = rby;
-    a.dpx[pos] = rbx - a.tree.rfx[i]; a.dpy[pos] = rby - a.tree.rfy[i];
+    const double dpx = rbx - a.tree.rfx[i], dpy = rby - a.tree.rfy[i];
+    a.dpx[pos] = dpx; a.dpy[pos] = dpy;
+    a.fx[pos] = (float)x; a.fy[pos] = (float)y; a.frx[pos] = (float)rbx; a.fry[pos] = (float)rby;
+    a.fdx[pos] = (float)dpx; a.fdy[pos] = (float)dpy;
     a.ang[pos] = a.tree.angPar[i];
     a.ca[pos] = a.tree.ca[i]; a.sa[pos] = a.tree.sa[i]; a.ce[pos] = a.tree.costE[i];
     a.sbin[pos] = a.bin[i];
@@ -236,6 +241,26 @@ __device__ __forceinline__ bool stage1_keep(float ex, float ey, float ce, float 
   return !(R < 0.0f) && !(d2 * 0.999999f > R * R);
 }
 
+// Float pre-test of feasibleNode (rrtplanner.cpp:271-289) on float copies of the node's reference end (frx, fry) and reference
+// direction (fdx, fdy): false = CERTAINLY infeasible in the reference's double arithmetic, true = undecided (the exact test
+// runs).  The heading test |angleDiff| <= pi/4 is dot >= |cross| of (sample - reference end) and the reference direction; in
+// float the difference dot - |cross| carries at most  P (4 d (|s| + |rb|) + 10 d |dn|)  of error, d = 2^-24, P = |dpx| + |dpy|,
+// |s| + |rb| the 1-norms of the two points, |dn| of their difference (rounding of the four inputs, of the subtraction, of two
+// products and a sum each) — the test below uses 6.7 d and 33 d.  The length test Lref >= 2.1 ref_res is decided in float 2 %
+// below the threshold when the coordinates are small enough for that to be safe.  NaNs and overflow fall to `true`.  Most
+// nodes near a sample fail feasibility (the parent's reference must point at the sample within 45 degrees): this keeps the
+// double-precision test, and the double node fields, off 95 % of the distance-bound survivors.
+__device__ __forceinline__ bool feasible_maybe(float fsx, float fsy, float frx, float fry, float fdx, float fdy, float feas_len2) {
+  const float dnx = fsx - frx, dny = fsy - fry;
+  const float dot = dnx * fdx + dny * fdy, crs = dnx * fdy - dny * fdx;
+  const float P = fabsf(fdx) + fabsf(fdy);
+  const float mag = fabsf(fsx) + fabsf(fsy) + fabsf(frx) + fabsf(fry);
+  const float E = P * (4.0e-7f * mag + 2.0e-6f * (fabsf(dnx) + fabsf(dny)));
+  if (dot - fabsf(crs) < -E) return false;
+  if (mag < 4096.0f && dnx * dnx + dny * dny < 0.98f * feas_len2) return false;
+  return true;
+}
+
 // The running top-10 of a sample lives in registers of lanes 0..9 of its warp (lane r = r-th best so far), ordered by
 // (key, node id).  Its last entry T bounds the search: the Dubins key is never below the Euclidean distance from
 // the node to the sample (checked over the whole float domain of dubinsDistance: key >= (1 - 3e-6) d outside the turning
@@ -245,11 +270,10 @@ __device__ __forceinline__ bool stage1_keep(float ex, float ey, float ce, float 
 // own position outwards, so T is tight after the first tile or two).  Three compaction stages keep the expensive
 // parts on full warps: distance bound (all nodes of a tile) -> feasibility (survivors) -> key (feasible survivors).
 __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const NearestArgs a) {
-  __shared__ double s_nx[NEAREST_TILE], s_ny[NEAREST_TILE], s_rbx[NEAREST_TILE], s_rby[NEAREST_TILE];
-  __shared__ double s_dpx[NEAREST_TILE], s_dpy[NEAREST_TILE], s_ang[NEAREST_TILE];
-  __shared__ float s_ca[NEAREST_TILE], s_sa[NEAREST_TILE], s_ce[NEAREST_TILE];
-  __shared__ float s_fx[NEAREST_TILE], s_fy[NEAREST_TILE];  // node positions rounded to float: stage 1 only
-  __shared__ int32_t s_id[NEAREST_TILE];
+  // a tile stages seven floats per node (position, reference end, reference direction, costE): all that the distance bound
+  // and the feasibility pre-test read; the double fields of the few survivors come straight from the sorted arrays
+  __shared__ float s_fx[NEAREST_TILE], s_fy[NEAREST_TILE], s_ce[NEAREST_TILE];
+  __shared__ float s_frx[NEAREST_TILE], s_fry[NEAREST_TILE], s_fdx[NEAREST_TILE], s_fdy[NEAREST_TILE];
   __shared__ uint16_t s_idx[NEAREST_WARPS][NEAREST_TILE];
   __shared__ uint16_t s_idx2[NEAREST_WARPS][NEAREST_TILE];
   __shared__ int s_start;
@@ -269,6 +293,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
   }
   const float fsx = (float)sx, fsy = (float)sy;
   const float slack = 1.0e-3f + 4.0e-7f * (fabsf(fsx) + fabsf(fsy));
+  const float feas_len2 = (float)(a.feas_len * a.feas_len);
   float lk = INFINITY;  // entry `lane` of the list (lanes >= 10 stay at +inf / INT_MAX and never take part)
   int lid = INT_MAX;
   float T = INFINITY;   // key and id of the 10th entry (warp-uniform)
@@ -304,6 +329,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
       // (dv == 0 for tiles without a lateral interval)
       want = !(0.999f * sqrtf(du * du + dv * dv) + (optimize ? so.tile_ce[t] : 0.0f) > T);
       axis_open = !(0.999f * du > T);
+
     }
     if (!__syncthreads_or(want ? 1 : 0)) {
       // Nobody needs this tile: it is skipped.  The DIRECTION is finished only when the axis distance alone rules the tile
@@ -321,28 +347,25 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
     const int n = min(NEAREST_TILE, so.n_nodes - base);
     if ((int)threadIdx.x < n) {
       const int g = base + threadIdx.x;
-      const double nxg = so.nx[g], nyg = so.ny[g];
-      s_nx[threadIdx.x] = nxg; s_ny[threadIdx.x] = nyg; s_fx[threadIdx.x] = (float)nxg; s_fy[threadIdx.x] = (float)nyg;
-      s_rbx[threadIdx.x] = so.rbx[g]; s_rby[threadIdx.x] = so.rby[g];
-      s_dpx[threadIdx.x] = so.dpx[g]; s_dpy[threadIdx.x] = so.dpy[g];
-      s_ang[threadIdx.x] = so.ang[g];
-      s_ca[threadIdx.x] = so.ca[g]; s_sa[threadIdx.x] = so.sa[g]; s_ce[threadIdx.x] = so.ce[g];
-      s_id[threadIdx.x] = so.node_id[g];
+      s_fx[threadIdx.x] = so.fx[g]; s_fy[threadIdx.x] = so.fy[g]; s_ce[threadIdx.x] = so.ce[g];
+      s_frx[threadIdx.x] = so.frx[g]; s_fry[threadIdx.x] = so.fry[g];
+      s_fdx[threadIdx.x] = so.fdx[g]; s_fdy[threadIdx.x] = so.fdy[g];
     }
     __syncthreads();
     if (live && want) {
-      // stage 1: distance bound against T
+      // stage 1: distance bound against T, then the float pre-test of feasibility for the nodes that pass it
       int c1 = 0;
       for (int i0 = 0; i0 < n; i0 += 32) {
         const int i = i0 + lane;
         bool keep = false;
         if (i < n) keep = stage1_keep(fsx - s_fx[i], fsy - s_fy[i], optimize ? s_ce[i] : 0.0f, T, slack);
+        if (keep) keep = feasible_maybe(fsx, fsy, s_frx[i], s_fry[i], s_fdx[i], s_fdy[i], feas_len2);
         const unsigned m = __ballot_sync(FULL_MASK, keep);
         if (keep) s_idx[warp][c1 + __popc(m & lt)] = (uint16_t)i;
         c1 += __popc(m);
       }
       __syncwarp();
-      // stage 2: feasibility of the survivors
+      // stage 2: feasibility of the survivors, in the reference's double arithmetic
       int c2 = 0;
       for (int q0 = 0; q0 < c1; q0 += 32) {
         const int q = q0 + lane;
@@ -350,7 +373,8 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
         bool f = false;
         if (q < c1) {
           i = s_idx[warp][q];
-          f = feasible_node(sx, sy, s_rbx[i], s_rby[i], s_dpx[i], s_dpy[i], s_ang[i], a.feas_len);
+          const int g = base + i;
+          f = feasible_node(sx, sy, so.rbx[g], so.rby[g], so.dpx[g], so.dpy[g], so.ang[g], a.feas_len);
         }
         const unsigned m = __ballot_sync(FULL_MASK, f);
         if (f) s_idx2[warp][c2 + __popc(m & lt)] = (uint16_t)i;
@@ -364,9 +388,10 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
         int idx = INT_MAX;
         if (q < c2) {
           const int i = s_idx2[warp][q];
-          key = dubins_key(sx, sy, s_nx[i], s_ny[i], s_ca[i], s_sa[i]);
+          const int g = base + i;
+          key = dubins_key(sx, sy, so.nx[g], so.ny[g], so.ca[g], so.sa[g]);
           if (optimize) key = s_ce[i] + key;  // rrtplanner.cpp:254
-          idx = s_id[i];
+          idx = so.node_id[g];
         }
         unsigned wantm = __ballot_sync(FULL_MASK, key < T || (key == T && idx < Tid));
         while (wantm) {
@@ -426,6 +451,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_topk_kernel(const Nea
   if (live) { sx = a.sample_xy[2 * j]; sy = a.sample_xy[2 * j + 1]; optimize = a.heuristic[j] != 0; }
   const float fsx = (float)sx, fsy = (float)sy;
   const float slack = 1.0e-3f + 4.0e-7f * (fabsf(fsx) + fabsf(fsy));
+  const float feas_len2 = (float)(a.feas_len * a.feas_len);
   float lk = INFINITY;  // entry `lane` of the list (lanes >= 10 stay at +inf / INT_MAX and never take part)
   int lid = INT_MAX;
   float T = INFINITY;   // key and id of the 10th entry (warp-uniform)
@@ -452,6 +478,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_topk_kernel(const Nea
         const int i = i0 + lane;
         bool keep = false;
         if (i < n) keep = stage1_keep(fsx - s_fx[i], fsy - s_fy[i], optimize ? s_ce[i] : 0.0f, T, slack);
+        if (keep) keep = feasible_maybe(fsx, fsy, (float)s_rbx[i], (float)s_rby[i], (float)s_dpx[i], (float)s_dpy[i], feas_len2);
         const unsigned m = __ballot_sync(FULL_MASK, keep);
         if (keep) s_idx[warp][c1 + __popc(m & lt)] = (uint16_t)i;
         c1 += __popc(m);
