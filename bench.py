@@ -203,7 +203,7 @@ def query_200ms_rounds(clrrt, device, K=16384, budget_ms=200.0):
             "scene": "C1: straight road, goal 50 m ahead, 10 static boxes, Prius parameters"}
 
 
-def query_200ms_k1(clrrt, device, budget_ms=200.0, chunk=16):
+def query_200ms_k1(clrrt, device, budget_ms=200.0, chunk=32):
     """The reference's own algorithm — one sample per expandTree, every sample seeing the nodes of the previous ones
     (rrt/src/motionplanner.cpp:39-43) — for 200 ms of wall clock on the C1 scene: clrrt_expand_sequential, `chunk`
     iterations per call with several samples in flight on the device, timer polled between calls.  Same draws (srand(1))

@@ -408,7 +408,8 @@ void MotionPlanner::planMotion(MotionRequest req) {
   const int round = std::max(samplesPerRound, 1);
   if (rrt_ && rrt_round_ != round) { delete rrt_; rrt_ = nullptr; }
   if (!rrt_) {
-    rrt_ = new MyRRT(req.goal, req.laneShifts, req.Cxy, req.bend, veh, params, req.vmax, carPose[4], device, treeCapacity, round);
+    // (the sequential mode keeps up to 64 samples in flight: its scratch is sized for that, not for one sample)
+    rrt_ = new MyRRT(req.goal, req.laneShifts, req.Cxy, req.bend, veh, params, req.vmax, carPose[4], device, treeCapacity, std::max(round, 64));
     rrt_round_ = round;
   } else {
     rrt_->bend = req.bend; rrt_->laneShifts = req.laneShifts; rrt_->Cxy = req.Cxy;
@@ -421,6 +422,7 @@ void MotionPlanner::planMotion(MotionRequest req) {
   RRT.carState = carPose;
   if (!params.commit_path) bestNodes.clear();                   // :28-30
   RRT.treeFull = false;
+  lastSeqWindows = lastSeqSpeculated = 0;
   initializeTree(RRT, veh, bestNodes, carPose);                 // :32
   lastCarried = (int)RRT.carried().size();
   lastInitialTree = RRT.treeSize();
@@ -434,7 +436,8 @@ void MotionPlanner::planMotion(MotionRequest req) {
       int n = sequentialChunk;
       if (maxIterations >= 0) { n = std::min(n, maxIterations - iter); if (n <= 0) break; }
       else if (std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() >= budget_ms) break;
-      expandTreeSequential(veh, RRT, n, sequentialWindow);
+      const clrrt_seq_stats ss = expandTreeSequential(veh, RRT, n, sequentialWindow);
+      lastSeqWindows += ss.windows; lastSeqSpeculated += ss.speculated;
       iter += n;
       if (RRT.treeFull) break;
     }
@@ -562,7 +565,7 @@ extern "C" int clrrt_host_simulate(const double* goal4, double vmax, const clrrt
 extern "C" int clrrt_host_planner_timings(void* h, double* ms6) {
   if (!h || !ms6) return CLRRT_ERR_ARG;
   for (int k = 0; k < 6; k++) ms6[k] = static_cast<clrrt::MotionPlanner*>(h)->lastMs[k];
-  return CLRRT_OK;
+  return static_cast<clrrt::MotionPlanner*>(h)->lastSeqWindows;  // >= 0: speculative windows the last query's expansion used
 }
 extern "C" int clrrt_host_planner_set_sequential(void* h, int chunk, int window) {
   if (!h || chunk < 1 || window < 0 || window > 64) return CLRRT_ERR_ARG;

@@ -167,7 +167,7 @@ struct MotionPlanner {
   PlannerParams params;
   int device = 0;
   int samplesPerRound = 1;        // 1 = the reference's sequential expandTree; >1 = snapshot rounds
-  int sequentialChunk = 16;       // samplesPerRound == 1: iterations per device call (1 = one clrrt_expand_round per iteration)
+  int sequentialChunk = 32;       // samplesPerRound == 1: iterations per device call (1 = one clrrt_expand_round per iteration)
   int sequentialWindow = 0;       // samples in flight inside a call (0 = adaptive), see clrrt_expand_sequential
   double budget_ms = 200;         // Timer(200), rrt/src/motionplanner.cpp:39 (wall clock here, CPU time upstream)
   int maxIterations = -1;         // >= 0: deterministic iteration budget instead of the timer (tests)
@@ -180,6 +180,7 @@ struct MotionPlanner {
   int lastCarried = 0;                // nodes of the previous best path the tree was initialised with (commit_path)
   int lastInitialTree = 0;            // tree size after initializeTree (1 = root only)
   int treeCapacity = 1 << 18;
+  int lastSeqWindows = 0, lastSeqSpeculated = 0;  // sequential mode: windows run / samples speculated in the last query
   double lastMs[6] = {0, 0, 0, 0, 0, 0};  // wall clock of the last query: parameters, obstacles, initial tree, expansion, best path, messages
   ~MotionPlanner();
 

@@ -43,10 +43,11 @@ int clrrt_host_simulate(const double* goal4, double vmax, const clrrt_obstacle* 
 void* clrrt_host_planner_create(int device, int samples_per_round, int commit_path, int tree_capacity);
 void clrrt_host_planner_destroy(void* h);
 /* samples_per_round == 1 (the reference's sequential loop): iterations per device call and samples in flight inside a call
- * (clrrt_expand_sequential).  chunk = 1 issues one clrrt_expand_round per iteration; default chunk 16, window 0 = adaptive.
+ * (clrrt_expand_sequential).  chunk = 1 issues one clrrt_expand_round per iteration; default chunk 32, window 0 = adaptive.
  * The tree is the same for every setting. */
 int clrrt_host_planner_set_sequential(void* h, int chunk, int window);
-/* wall-clock milliseconds of the last query by phase: parameters, obstacles, initial tree, expansion, best path, messages */
+/* wall-clock milliseconds of the last query by phase: parameters, obstacles, initial tree, expansion, best path, messages;
+ * returns the number of speculative windows the expansion used (sequential mode) */
 int clrrt_host_planner_timings(void* h, double* ms6);
 /* goal4 and obs in the car frame; sizes4 = {initial tree size, final tree size, best path nodes, expandTree calls} */
 int clrrt_host_planner_query(void* h, const double* world_state6, const double* goal4, double vmax, const clrrt_obstacle* obs,
