@@ -58,6 +58,9 @@ struct clrrt_ctx {
   ObsCold* d_cold = nullptr;
   ObsMoving* d_mov = nullptr;
   int obs_cap = 0;
+  unsigned char* h_obs_stage = nullptr;  // pinned staging of clrrt_set_obstacles
+  size_t obs_stage_cap = 0;
+  cudaEvent_t obs_stage_ev = nullptr;
   // round scratch
   double* d_samples = nullptr;
   uint8_t* d_heur = nullptr;
@@ -390,6 +393,8 @@ int clrrt_destroy(clrrt_ctx* ctx) {
   if (ctx->d_counts) cudaFree(ctx->d_counts);
   if (ctx->d_gather) cudaFree(ctx->d_gather);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+  if (ctx->h_obs_stage) cudaFreeHost(ctx->h_obs_stage);
+  if (ctx->obs_stage_ev) cudaEventDestroy(ctx->obs_stage_ev);
   if (ctx->h_ints) cudaFreeHost(ctx->h_ints);
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -570,13 +575,38 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
     CK(cudaMalloc((void**)&ctx->d_cell_items, (cell_items.size() + 8) * sizeof(uint16_t)));
     ctx->cell_items_cap = cell_items.size() + 8;
   }
-  CK(cudaStreamSynchronize(ctx->stream));
-  CK(cudaMemcpy(ctx->d_hot, hot.data(), hot.size() * sizeof(ObsHot), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(ctx->d_cold, cold.data(), cold.size() * sizeof(ObsCold), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(ctx->d_bnd, bnd.data(), bnd.size() * sizeof(ObsBound), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(ctx->d_cell_start, cell_start.data(), cell_start.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-  if (!cell_items.empty()) CK(cudaMemcpy(ctx->d_cell_items, cell_items.data(), cell_items.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-  if (!mov.empty()) CK(cudaMemcpy(ctx->d_mov, mov.data(), mov.size() * sizeof(ObsMoving), cudaMemcpyHostToDevice));
+  // one pinned staging buffer, asynchronous copies on the context's stream: nothing here blocks the host (a query with
+  // moving obstacles calls this every time, rrt/src/motionplanner.cpp:18).  The buffer is reused only after the copies of
+  // the previous call have completed (event).
+  {
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_hot = hot.size() * sizeof(ObsHot), b_cold = cold.size() * sizeof(ObsCold), b_bnd = bnd.size() * sizeof(ObsBound),
+                 b_cs = cell_start.size() * sizeof(int32_t), b_ci = cell_items.size() * sizeof(uint16_t), b_mov = mov.size() * sizeof(ObsMoving);
+    const size_t total = al(b_hot) + al(b_cold) + al(b_bnd) + al(b_cs) + al(b_ci) + al(b_mov);
+    if (ctx->obs_stage_ev) CK(cudaEventSynchronize(ctx->obs_stage_ev));
+    else CK(cudaEventCreateWithFlags(&ctx->obs_stage_ev, cudaEventDisableTiming));
+    if (total > ctx->obs_stage_cap) {
+      if (ctx->h_obs_stage) cudaFreeHost(ctx->h_obs_stage);
+      ctx->h_obs_stage = nullptr; ctx->obs_stage_cap = 0;
+      CK(cudaMallocHost((void**)&ctx->h_obs_stage, 2 * total));
+      ctx->obs_stage_cap = 2 * total;
+    }
+    unsigned char* q = ctx->h_obs_stage;
+    auto put = [&](void* dst, const void* src, size_t b) -> cudaError_t {
+      if (b == 0) return cudaSuccess;
+      memcpy(q, src, b);
+      const cudaError_t e = cudaMemcpyAsync(dst, q, b, cudaMemcpyHostToDevice, ctx->stream);
+      q += al(b);
+      return e;
+    };
+    CK(put(ctx->d_hot, hot.data(), b_hot));
+    CK(put(ctx->d_cold, cold.data(), b_cold));
+    CK(put(ctx->d_bnd, bnd.data(), b_bnd));
+    CK(put(ctx->d_cell_start, cell_start.data(), b_cs));
+    CK(put(ctx->d_cell_items, cell_items.data(), b_ci));
+    CK(put(ctx->d_mov, mov.data(), b_mov));
+    CK(cudaEventRecord(ctx->obs_stage_ev, ctx->stream));
+  }
   ctx->dprm.n_static = ns;
   ctx->dprm.n_moving = (int)mov.size();
   ctx->dprm.grid_nx = gnx; ctx->dprm.grid_ny = gny; ctx->dprm.grid_inv_cell = (float)(1.0 / cell);
@@ -602,15 +632,17 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
       build_pose_grid_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(
           ctx->d_bnd, ctx->d_cell_start, ctx->d_cell_items, ctx->d_pose_cells, ns, gnx, gny, sub, nh, (float)cell_f, infl,
           ctx->dprm.veh_hh, ctx->dprm.veh_hw, ctx->dprm.fine_margin);
-      CK(cudaGetLastError());
-      CK(cudaStreamSynchronize(ctx->stream));
+      CK(cudaGetLastError());  // (stream-ordered with the rounds that follow: no host synchronisation)
       ctx->dprm.pose_sub = sub; ctx->dprm.pose_nh = nh;
     }
   }
   // the broad-phase table is staged in shared memory when it leaves room for the other resident blocks
   ctx->dprm.static_in_smem = (ns > 0 && obstacle_table_bytes(ns) <= 48 * 1024) ? 1 : 0;
-  int rc = configure_launch(ctx);
-  if (rc != CLRRT_OK) return rc;
+  const size_t want_smem = ROLLOUT_SMEM_GB_BYTES + ROLLOUT_SMEM_VB_BYTES + (ctx->dprm.static_in_smem ? obstacle_table_bytes(ns) : 0);
+  if (want_smem != ctx->smem_bytes) {  // function attributes / occupancy only change with the staged table's size
+    int rc = configure_launch(ctx);
+    if (rc != CLRRT_OK) return rc;
+  }
   return upload_params(ctx);
 }
 
