@@ -8,11 +8,13 @@ mkdir -p $out
 if [ "$2" != "notests" ]; then
   python -m pytest tests -q -m gpu > $out/${tag}_pytest.log 2>&1; tail -3 $out/${tag}_pytest.log
 fi
-python bench.py --impl reference --steps 10 --warmup 2 > $out/${tag}_bench_reference.json 2> $out/${tag}_bench_reference.err
-python bench.py --steps 20 --warmup 3 > $out/${tag}_bench.json 2> $out/${tag}_bench.err || tail -5 $out/${tag}_bench.err
+# executed-FLOP counts of the round kernel first: bench.py's roofline divides them by the kernel time it measures live
 M=$(python scripts/rollout_ops.py --metrics)
 timeout 600 ncu --metrics $M --clock-control none -k regex:rollout_kernel -s 2 -c 1 --csv --log-file $out/${tag}_ops_fp64.csv python scripts/quick_round.py > $out/${tag}_ops_fp64.log 2>&1
 CLRRT_FP32=1 timeout 600 ncu --metrics $M --clock-control none -k regex:rollout_kernel -s 2 -c 1 --csv --log-file $out/${tag}_ops_fp32.csv python scripts/quick_round.py > $out/${tag}_ops_fp32.log 2>&1
+python scripts/rollout_ops.py $out/${tag}_ops_fp64.csv $out/${tag}_ops_fp32.csv > $out/${tag}_ops.log 2>&1 && cp profiles/r02_rollout_ops.json $out/${tag}_rollout_ops.json
+python bench.py --impl reference --steps 10 --warmup 2 > $out/${tag}_bench_reference.json 2> $out/${tag}_bench_reference.err
+python bench.py --steps 20 --warmup 3 > $out/${tag}_bench.json 2> $out/${tag}_bench.err || tail -5 $out/${tag}_bench.err
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --quick --no-c4 --sustain-seconds 0 > $out/${tag}_ncu_launches.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:rollout_kernel|nearest_sorted_kernel' -s 6 -c 2 -o $out/${tag}_prof -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline --quick --no-c4 --sustain-seconds 0 > $out/${tag}_ncu_full.log 2>&1
 ncu -i $out/${tag}_prof.ncu-rep --page raw --csv > $out/${tag}_prof_raw.csv 2>/dev/null

@@ -1,23 +1,24 @@
 """Turn gpurun_out/launches.csv and gpurun_out/prof.ncu-rep into the tracked summaries under profiles/."""
 import collections, csv, io, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+pre = (sys.argv[2] + "_") if len(sys.argv) > 2 else ""   # gpurun_out/<pre>launches.csv, gpurun_out/<pre>prof.ncu-rep
 out = os.path.join(ROOT, "profiles")
 os.makedirs(out, exist_ok=True)
-rows = [r for r in csv.reader(open(os.path.join(ROOT, "gpurun_out", "launches.csv"))) if len(r) > 10]
+rows = [r for r in csv.reader(open(os.path.join(ROOT, "gpurun_out", pre + "launches.csv"))) if len(r) > 10]
 hdr = rows[0]; ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
 agg = collections.OrderedDict()
 for r in rows[1:]:
     agg.setdefault(r[ik].split("(")[0][:70], []).append(float(r[iv].replace(",", "")))
 tot = sum(sum(v) for v in agg.values())
 with open(os.path.join(out, f"{tag}_launches.md"), "w") as f:
-    f.write(f"# ncu launch list ({tag}): `python bench.py --steps 2 --warmup 1 --no-cpu-baseline`\n\n"
+    f.write(f"# ncu launch list ({tag}): `python bench.py --steps 2 --warmup 1 --no-cpu-baseline --quick --no-c4 --sustain-seconds 0`\n\n"
             "`ncu --metrics gpu__time_duration.sum --clock-control none` — per-launch device time (cold-cache, serialised: compare shares).\n"
-            "Includes the untimed set-up (tree growth rounds of 8192 samples) and the e2e leg.\n\n| kernel | launches | total ms | max ms | share |\n|---|---|---|---|---|\n")
+            "Includes the warm-up rounds, the e2e leg (export_nodes) and the one extra round whose tree is digested.\n\n| kernel | launches | total ms | max ms | share |\n|---|---|---|---|---|\n")
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         f.write(f"| `{k}` | {len(v)} | {sum(v)/1e6:.3f} | {max(v)/1e6:.3f} | {100*sum(v)/tot:.1f}% |\n")
 print(open(os.path.join(out, f"{tag}_launches.md")).read())
-rep = os.path.join(ROOT, "gpurun_out", "prof.ncu-rep")
+rep = os.path.join(ROOT, "gpurun_out", pre + "prof.ncu-rep")
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 r = list(csv.reader(io.StringIO(raw)))
 h = r[0]
@@ -40,7 +41,7 @@ want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed"]
 with open(os.path.join(out, f"{tag}_rollout_kernel_ncu.md"), "w") as f:
     f.write(f"# ncu --set full ({tag}): candidate search and rollout kernel of one C3 round (65536 samples, 1000 obstacles, 4096-node tree)\n\n"
-            "`ncu --set full --clock-control none --import-source on -k 'regex:rollout_kernel|nearest_sorted_kernel' -s 6 -c 2 python bench.py --steps 2 --warmup 1 --no-cpu-baseline`\n\n")
+            "`ncu --set full --clock-control none --import-source on -k 'regex:rollout_kernel|nearest_sorted_kernel' -s 6 -c 2 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --quick --no-c4 --sustain-seconds 0`\n\n")
     cols = [i for i in range(2, len(r))]
     f.write("| metric | unit | " + " | ".join(f"launch {i-2}" for i in cols) + " |\n|---|---|" + "---|" * len(cols) + "\n")
     for w in want:
