@@ -1,5 +1,13 @@
 // refmath.cuh — float transcendental functions with bit-for-bit the results of the reference platform.
 //
+// PROVENANCE / LICENCE NOTE.  The GNU C Library is distributed under the LGPL v2.1 or later; its sinf / cosf / exp come from
+// ARM Optimized Routines (MIT OR Apache-2.0 WITH LLVM-exception), atanf / acosf / asinf from FreeBSD msun (Sun Microsystems'
+// permissive notice), sin / cos / tan from the IBM Accurate Mathematical Library (LGPL).  Nothing was copied from the
+// reference repository (it contains no libm).  The routines below were written from the published algorithms against the
+// behaviour of the installed library (tests/test_refmath.py sweeps them against it); the numeric tables are constants
+// extracted from the installed libm by scripts/gen_refmath64_tables.py.  A redistributor who treats restated algorithms
+// and extracted tables as derived work of glibc should ship these three files under the LGPL.
+//
 // The reference computes its Dubins metric (rrt/src/rrtplanner.cpp:371-406) and OBB geometry
 // (rrt/src/old_collisioncheck.cpp:56-65) in float through the C library: cosf, sinf, atan2f, acosf, asinf of
 // glibc 2.39 libm on x86-64.  Candidate order and separating-axis signs hang on the last bit of

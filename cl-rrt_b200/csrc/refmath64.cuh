@@ -1,5 +1,13 @@
 // refmath64.cuh — double sin / cos / tan with bit-for-bit the results of the reference platform.
 //
+// PROVENANCE / LICENCE NOTE.  The GNU C Library is distributed under the LGPL v2.1 or later; its sinf / cosf / exp come from
+// ARM Optimized Routines (MIT OR Apache-2.0 WITH LLVM-exception), atanf / acosf / asinf from FreeBSD msun (Sun Microsystems'
+// permissive notice), sin / cos / tan from the IBM Accurate Mathematical Library (LGPL).  Nothing was copied from the
+// reference repository (it contains no libm).  The routines below were written from the published algorithms against the
+// behaviour of the installed library (tests/test_refmath.py sweeps them against it); the numeric tables are constants
+// extracted from the installed libm by scripts/gen_refmath64_tables.py.  A redistributor who treats restated algorithms
+// and extracted tables as derived work of glibc should ship these three files under the LGPL.
+//
 // The reference integrates its vehicle model in double through the C library: sin, cos (heading) and tan (steering angle)
 // of glibc 2.39 on x86-64 (rrt/src/simulation.cpp:11-25, rrt/src/controller.cpp:56-57).  CUDA's own double routines agree
 // with glibc's to the last ulp in most calls, not in all; the states then drift apart by ~1e-13, which is harmless except

@@ -38,6 +38,15 @@ int clrrt_host_simulate(const double* goal4, double vmax, const clrrt_obstacle* 
                         int n_state, const double* ref_x, const double* ref_y, double* ref_v, int n_ref, int goal_biased,
                         int gen_profile, double Vstart, double* costs2, int32_t* flags3, double* last_state10);
 
+/* Curved-road mode, host side (cl-rrt_b200/host/clrrt_road.hpp; rrt/src/transformations.cpp:20-287, rrt/src/rrtplanner.cpp
+ * :204-224 — present upstream but not reachable from the shipped planMotion).  clrrt_host_road_transform applies one of the
+ * road-frame transforms in place to n records (x, y, heading, delta): what = 0 point car->road, 1 point road->car, 2 pose
+ * car->road, 3 pose road->car, 4 state car->road, 5 state road->car (Prius), 6 closest point on the road's arc.
+ * clrrt_host_sample_on_lane: K x { sampleOnLane, heuristic draw } on rand(), v = the car's speed (look-ahead distance). */
+int clrrt_host_road_transform(int what, const double* Cxy3, const double* Cxs3, double* xyhd, int n);
+int clrrt_host_sample_on_lane(const double* Cxy3, const double* lane_shifts, int n_lanes, double Lmax, double v, int K,
+                              double* sample_xy, uint8_t* heuristic);
+
 /* Persistent planner: consecutive queries on one device context with MotionPlanner::bestNodes kept between them
  * (commit_path != 0: the next tree is initialised from the previous best path, rrt/src/rrtplanner.cpp:50-94). */
 void* clrrt_host_planner_create(int device, int samples_per_round, int commit_path, int tree_capacity);

@@ -410,6 +410,38 @@ int ref_simulate(const double* state10, const double* rx, const double* ry, doub
   if (traj) for (int i = 0; i < rows; i++) for (int k = 0; k < 10; k++) traj[10 * i + k] = sim.stateArray[i][k];
   return (int)sim.stateArray.size();
 }
+// Road-frame transforms of rrt/src/transformations.cpp:20-202 on n records (x, y, heading, delta), in place; `what` as in
+// clrrt_host_road_transform (include/clrrt_host.h).
+int ref_road_transform(int what, const double* Cxy3, const double* Cxs3, double* xyhd, int n) {
+  vector<double> Cxy(Cxy3, Cxy3 + 3), Cxs(Cxs3, Cxs3 + 3);
+  for (int i = 0; i < n; i++) {
+    double* p = xyhd + 4 * (size_t)i;
+    if (what == 0) transformPointCarToRoad(p[0], p[1], Cxy, Cxs);
+    else if (what == 1) transformPointRoadToCar(p[0], p[1], Cxy, Cxs);
+    else if (what == 2) transformPoseCarToRoad(p[0], p[1], p[2], Cxy, Cxs);
+    else if (what == 3) transformPoseRoadToCar(p[0], p[1], p[2], Cxy, Cxs);
+    else if (what == 6) { vector<double> a = findClosestPointOnArc(p[0], p[1], Cxy); p[0] = a[0]; p[1] = a[1]; }
+    else {
+      state_type s = {p[0], p[1], p[2], p[3], 0, 0};
+      if (what == 4) transformStateCarToRoad(s, Cxy, Cxs, g_veh); else transformStateRoadToCar(s, Cxy, Cxs, g_veh);
+      for (int k = 0; k < 4; k++) p[k] = s[k];
+    }
+  }
+  return 0;
+}
+// sampleOnLane (rrt/src/rrtplanner.cpp:204-224) + the heuristic draw, K times; v sets the look-ahead global ctrl_dla.
+int ref_sample_on_lane(const double* Cxy3, const double* lane_shifts, int n_lanes, double Lmax, double v, int K,
+                       double* sample_xy, unsigned char* heuristic) {
+  vector<double> Cxy(Cxy3, Cxy3 + 3), ls(lane_shifts, lane_shifts + n_lanes);
+  updateLookahead(v);
+  for (int j = 0; j < K; j++) {
+    geometry_msgs::Point s = sampleOnLane(Cxy, ls, Lmax);
+    sample_xy[2 * j] = s.x; sample_xy[2 * j + 1] = s.y;
+    double r = static_cast<double>(rand()) / (static_cast<double>(RAND_MAX / (1)));
+    heuristic[j] = !(r <= 0.7);
+  }
+  return 0;
+}
 // sampleAroundVehicle + the heuristic draw, in the order of rrt/src/rrtplanner.cpp:133-143.
 void ref_draw_samples(int K, double* sample_xy, unsigned char* heuristic, double* r_out) {
   for (int j = 0; j < K; j++) {

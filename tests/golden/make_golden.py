@@ -7,7 +7,7 @@ Every array is produced by libclrrt_ref_defined.so (reference + the documented U
 cross-checked here against the unmodified libclrrt_ref.so on all untainted rollouts (bit-for-bit); the mask of
 rows where the unmodified build differs is stored as `unmod_differs` and must be a subset of `tainted`.
 Golden sets follow SURVEY.md §8c: G0 known answers, G1 rollouts (C2), G2 candidate lists, G3 whole-query
-replay at K=1, G4 dense-scene verdicts (C3), G5 receding-horizon loop with carried-over trees (C5), G6 curved-road cost (bend).
+replay at K=1, G4 dense-scene verdicts (C3), G5 receding-horizon loop with carried-over trees (C5), G6 curved-road cost (bend), G7 road-frame transforms and lane samples.
 """
 import json
 import os
@@ -213,13 +213,49 @@ def g5(queries=100, iters=100):
     np.savez_compressed(os.path.join(HERE, "g5_replan.npz"), **out)
 
 
+def g7():
+    """Curved-road mode on the host: the reference's road-frame transforms
+    (rrt/src/transformations.cpp:20-202) and sampleOnLane (rrt/src/rrtplanner.cpp:204-224) on fixed inputs."""
+    import ctypes as C
+    ref = C.CDLL(os.path.join(os.path.dirname(HERE), "..", "oracle", "_ref", "libclrrt_ref.so"))
+    ref.ref_init()
+    ref.ref_road_transform.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    ref.ref_sample_on_lane.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    Cxy = np.array([-0.0035, 0.08, -1.0])
+    x = np.linspace(0, 80, 400)
+    dy = 2 * Cxy[0] * x + Cxy[1]
+    S = np.concatenate([[0], np.cumsum(np.sqrt(1 + ((dy[1:] + dy[:-1]) / 2) ** 2) * np.diff(x))])
+    Cxs = np.ascontiguousarray(np.polyfit(x, S, 2))
+    rng = np.random.default_rng(21)
+    n = 512
+    px = rng.uniform(2, 70, n)
+    inputs = np.column_stack([px, Cxy[0] * px ** 2 + Cxy[1] * px + Cxy[2] + rng.uniform(-6, 6, n), rng.uniform(-0.6, 0.6, n),
+                              rng.uniform(-0.3, 0.3, n)])
+    out = {"Cxy": Cxy, "Cxs": Cxs, "inputs": inputs}
+    for what in range(7):
+        r = inputs.copy()
+        ref.ref_road_transform(what, Cxy.ctypes.data, Cxs.ctypes.data, r.ctypes.data, n)
+        out[f"out{what}"] = r
+    lanes = np.array([-3.5, 0.0, 3.5])
+    K = 256
+    s, h = np.zeros((K, 2)), np.zeros(K, np.uint8)
+    C.CDLL(None).srand(C.c_uint(7))
+    ref.ref_sample_on_lane(Cxy.ctypes.data, lanes.ctypes.data, 3, 60.0, 4.0, K, s.ctypes.data, h.ctypes.data)
+    out.update(lanes=lanes, lane_samples=s, lane_heuristic=h)
+    np.savez_compressed(os.path.join(HERE, "g7_road.npz"), **out)
+    print("g7: road-frame transforms x 7,", K, "lane samples")
+
+
 if __name__ == "__main__":
+    if "--only-g7" in sys.argv:
+        g7()
+        sys.exit(0)
     if "--only-g5" in sys.argv:
         g5()
         sys.exit(0)
     if "--only-g6" in sys.argv:
         g6()
         sys.exit(0)
-    g0(); g1_g2(); g3(); g4(); g5(); g6()
+    g0(); g1_g2(); g3(); g4(); g5(); g6(); g7()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
