@@ -495,8 +495,9 @@ def run_ours(args):
     h_smp = torch.from_numpy(smp).pin_memory()
     h_heu = torch.from_numpy(heu).pin_memory()
     np_smp, np_heu = h_smp.numpy(), h_heu.numpy()  # views of the pinned buffers
-    h_nodes = torch.empty(2 * K_ROUND * world * clrrt.RECORD_BYTES, dtype=torch.uint8).pin_memory()
-    np_nodes = h_nodes.numpy().view(clrrt.NODE_DTYPE)  # pinned destination of the e2e leg's result read-back
+    # pinned destinations of the e2e leg's result read-back: two, the copy of round r overlaps round r + 1
+    h_nodes = [torch.empty(2 * K_ROUND * world * clrrt.RECORD_BYTES, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    np_nodes = [h.numpy().view(clrrt.NODE_DTYPE) for h in h_nodes]
 
     def one_round(dev_inputs=True):
         if dev_inputs:
@@ -519,8 +520,10 @@ def run_ours(args):
         e0.record(stream)
         while done < steps or (min_seconds > 0 and world == 1 and time.perf_counter() - t_wall < min_seconds):
             st = one_round(dev_inputs)
-            if download:  # the step's result: the nodes the round appended (all ranks' nodes: every rank holds the full tree)
-                nodes = pl.tree_download_range(n0, pl.tree_size() - n0, out=np_nodes)
+            if download:
+                # the step's result: the nodes the round appended (all ranks' nodes: every rank holds the full tree), read back
+                # into pinned memory on a second stream while the next round runs; the last copy is awaited inside the timed region
+                nodes = pl.tree_download_range_async(n0, pl.tree_size() - n0, np_nodes[done & 1])
                 d2h = nodes.nbytes + ctypes.sizeof(clrrt.RoundStats)
             pl.tree_truncate(n0)
             tot_steps += st.sim_steps
@@ -532,6 +535,8 @@ def run_ours(args):
             # the e2e leg adds export_nodes for the read-back
             launches += 15 + (1 if download else 0)
             done += 1
+        if download:
+            pl.download_wait()
         e1.record(stream)
         if world > 1:
             dist.barrier()

@@ -107,6 +107,8 @@ def load_library():
     lib.clrrt_set_grid_cell.argtypes = [vp, dp]
     lib.clrrt_set_nearest_mode.argtypes = [vp, ip]
     lib.clrrt_tree_download_range.argtypes = [vp, ip, ip, vp]
+    lib.clrrt_tree_download_range_async.argtypes = [vp, ip, ip, vp]
+    lib.clrrt_download_wait.argtypes = [vp]
     lib.clrrt_draw_samples.argtypes = [vp, ip, vp, vp]
     lib.clrrt_expand_sequential.argtypes = [vp, vp, vp, ip, ip, C.POINTER(SeqStats)]
     lib.clrrt_comm_unique_id.argtypes = [vp, ip]
@@ -289,6 +291,15 @@ class Planner:
         out = np.zeros(count, NODE_DTYPE) if out is None else out[:count]
         self._ck(self.lib.clrrt_tree_download_range(self.h, first, count, out.ctypes.data))
         return out
+
+    def tree_download_range_async(self, first, count, out):
+        """Stage nodes [first, first + count) now, copy them to `out` (a view of PINNED memory) beside the next round;
+        download_wait() before reading `out`."""
+        self._ck(self.lib.clrrt_tree_download_range_async(self.h, first, count, out.ctypes.data))
+        return out[:count]
+
+    def download_wait(self):
+        self._ck(self.lib.clrrt_download_wait(self.h))
 
     def tree_download_records(self):
         t = self.tree_download()

@@ -73,6 +73,9 @@ struct clrrt_ctx {
   float *d_tile_ulo = nullptr, *d_tile_uhi = nullptr, *d_tile_vlo = nullptr, *d_tile_vhi = nullptr, *d_tile_ce = nullptr;
   NodeRecord* d_export = nullptr;    // staging of clrrt_tree_download_range
   size_t export_cap = 0;
+  cudaStream_t copy_stream = nullptr;   // clrrt_tree_download_range_async: device-to-host copies beside the next round
+  cudaEvent_t ev_export = nullptr, ev_copied = nullptr;
+  bool copy_pending = false;
   void* d_init = nullptr;            // prepared rollouts of a round (setup_kernel) + per-thread scratch records
   size_t init_stride = 0;
   uint8_t* d_bucket = nullptr;
@@ -393,6 +396,9 @@ int clrrt_destroy(clrrt_ctx* ctx) {
   if (ctx->d_counts) cudaFree(ctx->d_counts);
   if (ctx->d_gather) cudaFree(ctx->d_gather);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  if (ctx->ev_export) cudaEventDestroy(ctx->ev_export);
+  if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
   if (ctx->h_obs_stage) cudaFreeHost(ctx->h_obs_stage);
   if (ctx->obs_stage_ev) cudaEventDestroy(ctx->obs_stage_ev);
   if (ctx->h_ints) cudaFreeHost(ctx->h_ints);
@@ -586,7 +592,10 @@ int clrrt_set_obstacles(clrrt_ctx* ctx, const clrrt_obstacle* host, int n) {
     if (ctx->obs_stage_ev) CK(cudaEventSynchronize(ctx->obs_stage_ev));
     else CK(cudaEventCreateWithFlags(&ctx->obs_stage_ev, cudaEventDisableTiming));
     if (total > ctx->obs_stage_cap) {
-      if (ctx->h_obs_stage) cudaFreeHost(ctx->h_obs_stage);
+      if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  if (ctx->ev_export) cudaEventDestroy(ctx->ev_export);
+  if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
+  if (ctx->h_obs_stage) cudaFreeHost(ctx->h_obs_stage);
       ctx->h_obs_stage = nullptr; ctx->obs_stage_cap = 0;
       CK(cudaMallocHost((void**)&ctx->h_obs_stage, 2 * total));
       ctx->obs_stage_cap = 2 * total;
@@ -691,6 +700,7 @@ int clrrt_tree_download_range(clrrt_ctx* ctx, int first, int n, clrrt_node* host
   if (!ctx || !host || first < 0 || n < 0 || first + n > ctx->n_tree) return CLRRT_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   if (n == 0) return CLRRT_OK;
+  if (ctx->copy_pending) { CK(cudaEventSynchronize(ctx->ev_copied)); ctx->copy_pending = false; }
   static_assert(sizeof(clrrt_node) == sizeof(NodeRecord), "clrrt_node and NodeRecord share one layout");
   if ((size_t)n > ctx->export_cap) {
     if (ctx->d_export) cudaFree(ctx->d_export);
@@ -704,6 +714,43 @@ int clrrt_tree_download_range(clrrt_ctx* ctx, int first, int n, clrrt_node* host
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(host, ctx->d_export, (size_t)n * sizeof(NodeRecord), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return CLRRT_OK;
+}
+
+// Asynchronous form: the export kernel runs on the context's stream (ordered before whatever the caller launches next, so
+// the exported range may be truncated and re-grown right away), the device-to-host copy on a second stream, so that it
+// overlaps the next round.  `host` should be pinned memory and must stay valid until clrrt_download_wait; at most one
+// download is in flight (a second call waits for the first).
+int clrrt_tree_download_range_async(clrrt_ctx* ctx, int first, int n, clrrt_node* host) {
+  if (!ctx || !host || first < 0 || n < 0 || first + n > ctx->n_tree) return CLRRT_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_export, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
+  }
+  if (ctx->copy_pending) { CK(cudaEventSynchronize(ctx->ev_copied)); ctx->copy_pending = false; }
+  if (n == 0) return CLRRT_OK;
+  if ((size_t)n > ctx->export_cap) {
+    if (ctx->d_export) cudaFree(ctx->d_export);
+    ctx->d_export = nullptr;
+    ctx->export_cap = 0;
+    const size_t cap = std::max<size_t>((size_t)n, 1024) * 2;
+    CK(cudaMalloc((void**)&ctx->d_export, cap * sizeof(NodeRecord)));
+    ctx->export_cap = cap;
+  }
+  export_nodes_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->tree, first, n, ctx->d_export);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev_export, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_export, 0));
+  CK(cudaMemcpyAsync(host, ctx->d_export, (size_t)n * sizeof(NodeRecord), cudaMemcpyDeviceToHost, ctx->copy_stream));
+  CK(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+  ctx->copy_pending = true;
+  return CLRRT_OK;
+}
+int clrrt_download_wait(clrrt_ctx* ctx) {
+  if (!ctx) return CLRRT_ERR_ARG;
+  if (ctx->copy_pending) { CK(cudaEventSynchronize(ctx->ev_copied)); ctx->copy_pending = false; }
   return CLRRT_OK;
 }
 

@@ -146,6 +146,11 @@ int clrrt_tree_size(const clrrt_ctx* ctx);
 int clrrt_tree_truncate(clrrt_ctx* ctx, int n); /* drop nodes >= n (bench: same snapshot every round) */
 int clrrt_tree_download(clrrt_ctx* ctx, clrrt_node* host, int cap, int* n);
 int clrrt_tree_download_range(clrrt_ctx* ctx, int first, int count, clrrt_node* host);
+/* Same without waiting: the nodes are staged on the context's stream (the range may be truncated and re-grown by the very
+ * next call) and copied to `host` (pinned memory, valid until clrrt_download_wait) on a second stream, beside the next
+ * round.  One download in flight per context. */
+int clrrt_tree_download_range_async(clrrt_ctx* ctx, int first, int count, clrrt_node* host);
+int clrrt_download_wait(clrrt_ctx* ctx);
 
 /* == sortNodesExplore (heuristic[j]==0) / sortNodesOptimize (==1), rrt/src/rrtplanner.cpp:227-268, for K samples
  * against the current tree: up to CLRRT_SORT_LIMIT feasible node ids in increasing key order (ties: lower id),

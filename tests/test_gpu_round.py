@@ -94,3 +94,29 @@ def test_empty_and_degenerate_rounds(clrrt, planner):
     assert st.nodes_added == 0 and st.rollouts == 0 and planner.tree_size() == 1
     with pytest.raises(clrrt.ClrrtError):
         planner.expand_round(np.zeros((planner.max_round + 1, 2)), np.zeros(planner.max_round + 1, np.uint8))
+
+
+def test_async_download_equals_sync_download(clrrt, planner):
+    """clrrt_tree_download_range_async: the nodes staged before the range is truncated and re-grown by the next round arrive
+    unchanged (the copy runs on a second stream beside that round)."""
+    import torch
+    car, goal = (0, 0, 0, 0, 2, 0), (50, 0, 0, 0)
+    planner.set_query(car, goal, 5.0)
+    planner.set_obstacles(scene_c1_boxes())
+    planner.tree_reset(clrrt.root_node(car))
+    s, h = clrrt.draw_samples(goal, 3 * 4096, seed=9)
+    planner.expand_round(s[:4096], h[:4096])
+    n0 = planner.tree_size()
+    pinned = [torch.empty(2 * 4096 * clrrt.RECORD_BYTES, dtype=torch.uint8).pin_memory().numpy().view(clrrt.NODE_DTYPE) for _ in range(2)]
+    want = []
+    for r in range(1, 3):
+        planner.expand_round(s[r * 4096:(r + 1) * 4096], h[r * 4096:(r + 1) * 4096])
+        n = planner.tree_size() - n0
+        want.append(planner.tree_download_range(n0, n).copy())
+        got = planner.tree_download_range_async(n0, n, pinned[r - 1])
+        planner.tree_truncate(n0)                                            # the next round overwrites the range at once
+        if r == 1:
+            continue
+    planner.download_wait()
+    assert pinned[1][:len(want[1])].tobytes() == want[1].tobytes()
+    assert pinned[0][:len(want[0])].tobytes() == want[0].tobytes()
