@@ -1435,6 +1435,7 @@ int clrrt_comm_attach(clrrt_ctx* ctx, void* nccl_comm, int rank, int world) {
   if (!ctx || !nccl_comm || world < 1 || world > CLRRT_MAX_WORLD || rank < 0 || rank >= world) return CLRRT_ERR_ARG;
   if (!nccl_api(&ctx->err)) return CLRRT_ERR_STATE;
   CK(cudaSetDevice(ctx->device));
+  if (ctx->comm && ctx->own_comm) { const NcclApi* nc = nccl_api(nullptr); if (nc) nc->CommDestroy(ctx->comm); }
   ctx->comm = (ncclComm_t)nccl_comm; ctx->own_comm = false; ctx->rank = rank; ctx->world = world;
   return comm_buffers(ctx);
 }
@@ -1448,6 +1449,7 @@ int clrrt_comm_init(clrrt_ctx* ctx, const void* id, int bytes, int rank, int wor
   memcpy(&u, id, sizeof u);
   ncclComm_t c = nullptr;
   NCK(nc->CommInitRank(&c, world, u, rank));
+  if (ctx->comm && ctx->own_comm) nc->CommDestroy(ctx->comm);  // a second init replaces the first communicator
   ctx->comm = c; ctx->own_comm = true; ctx->rank = rank; ctx->world = world;
   return comm_buffers(ctx);
 }
