@@ -218,6 +218,7 @@ def query_200ms_k1(clrrt, device, budget_ms=200.0, chunk=32):
     clrrt.draw_samples(C1_GOAL, 1, seed=1)
     ctypes.CDLL(None).srand(ctypes.c_uint(1))
     it = steps = windows = spec = 0
+    dev = [0.0, 0.0, 0.0, 0.0]
     t0 = time.perf_counter()
     while (time.perf_counter() - t0) * 1e3 < budget_ms:
         s, h = clrrt.draw_samples(C1_GOAL, chunk)
@@ -226,12 +227,15 @@ def query_200ms_k1(clrrt, device, budget_ms=200.0, chunk=32):
         steps += st.sim_steps
         windows += st.windows
         spec += st.speculated
+        for k, v in enumerate((st.ms_search, st.ms_prepare, st.ms_rollout, st.ms_commit)):
+            dev[k] += v
     wall = (time.perf_counter() - t0) * 1e3
     nodes = pl.tree_size()
     path = len(pl.best_path())
     pl.close()
     return {"nodes": int(nodes), "iterations": it, "sim_steps": int(steps), "wall_ms": wall, "budget_ms": budget_ms,
             "windows": windows, "samples_speculated": spec, "best_path_nodes": int(path),
+            "device_ms": {"search": dev[0], "prepare": dev[1], "rollout_kernel": dev[2], "select_tie_commit": dev[3]},
             "algorithm": "the reference's sequential expandTree loop (tree identical to the reference's for the same number of "
                          "iterations), speculative windows on the device",
             "scene": "C1: straight road, goal 50 m ahead, 10 static boxes, Prius parameters"}

@@ -1250,8 +1250,15 @@ int clrrt_expand_sequential(clrrt_ctx* ctx, const double* sample_xy, const uint8
       c.feas_len = ctx->dprm.feas_len; c.counters = ctx->d_counters; c.out = ctx->d_ints + 8;
       seq_commit_kernel<<<1, SEQ_THREADS, 0, st>>>(c);
       CK(cudaGetLastError());
+      CK(cudaEventRecord(ctx->ev[4], st));
       CK(cudaMemcpyAsync(ctx->h_ints + 8, ctx->d_ints + 8, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
+      {
+        float a = 0, b = 0, c2 = 0, d = 0;  // device time of the window's phases (CUDA events of round_core)
+        cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]); cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[5]);
+        cudaEventElapsedTime(&c2, ctx->ev[5], ctx->ev[2]); cudaEventElapsedTime(&d, ctx->ev[2], ctx->ev[4]);
+        acc.ms_search += a; acc.ms_prepare += b; acc.ms_rollout += c2; acc.ms_commit += d;
+      }
       const int committed = ctx->h_ints[8], appended = ctx->h_ints[9], stop = ctx->h_ints[10];
       ctx->n_tree += appended;
       acc.windows++; acc.nodes_added += appended; acc.speculated += w;

@@ -27,101 +27,109 @@ RoadFrame::RoadFrame(const std::vector<double>& Cxy, const std::vector<double>& 
 }
 
 void RoadFrame::closestPointOnArc(double Xcar, double Ycar, double& Xarc, double& Yarc) const {
-  const std::vector<double>& Cxy = Cxy_;
-  // closed-form root of the cubic d/dx |P - road(x)|^2 = 0 (upstream: "solved symbolically in MATLAB"); the temporaries are
-  // float upstream and stay float here
-  float t2 = std::abs(Cxy[0]);
-  float t3 = pow(Cxy[0], 3);
-  float t4 = pow(Cxy[1], 2);
-  float t5 = Xcar * Cxy[0] * 2.0;
-  float t6 = Ycar * Cxy[0] * 4.0;
-  float t8 = Cxy[0] * Cxy[2] * 4.0;
-  float t11 = sqrt(3.0);
-  float t7 = pow(t2, 3);
-  float t9 = 1.0 / t3;
-  float t10 = -t8;
-  float t12 = Cxy[1] + t5;
-  float t13 = pow(t12, 2);
-  float t14 = Cxy[1] * t7 * 9.0;
-  float t15 = Xcar * Cxy[0] * t7 * 18;
-  float t17 = t4 + t6 + t10 - 2.0;
-  float t16 = t13 * 27;
-  float t18 = pow(t17, 3);
-  float t19 = -t18;
-  float t20 = t16 + t19;
-  float t21 = sqrt(t20);
-  float t22 = t3 * t11 * t21;
-  float t23 = t14 + t15 + t22;
-  float t24 = t9 * t23;
-  Xarc = (pow(t24, 1.0 / 3.0) * 0.2403749283845681) / t2 - Cxy[1] / (Cxy[0] * 2.0) +
-         1.0 / pow(Cxy[0], 2) * t2 * t17 * 1.0 / pow(t24, 1.0 / 3.0) * 0.3466806371753173;
-  Yarc = Cxy[0] * pow(Xarc, 2) + Cxy[1] * Xarc + Cxy[2];
+  // Foot point of P on the parabola: the real root of d/dx |P - road(x)|^2 = 0, a depressed cubic solved in closed form
+  // (Cardano).  Upstream's generated code keeps every intermediate in float; the same roundings are kept here, one named
+  // float per intermediate, so the root — and everything derived from it — is bit-identical.
+  const double a = Cxy_[0], b = Cxy_[1], c = Cxy_[2];
+  const float abs_a = std::abs(a);
+  const float abs_a3 = pow(abs_a, 3);
+  const float a3 = pow(a, 3);
+  const float inv_a3 = 1.0 / a3;
+  const float b2 = pow(b, 2);
+  const float two_ax = Xcar * a * 2.0;
+  const float four_ay = Ycar * a * 4.0;
+  const float four_ac = a * c * 4.0;
+  const float neg_four_ac = -four_ac;
+  const float root3 = sqrt(3.0);
+  const float lin = b + two_ax;                       // slope-like term of the cubic
+  const float lin2 = pow(lin, 2);
+  const float term_b = b * abs_a3 * 9.0;
+  const float term_x = Xcar * a * abs_a3 * 18;
+  const float q = b2 + four_ay + neg_four_ac - 2.0;   // the cubic's linear coefficient (scaled)
+  const float lin2_27 = lin2 * 27;
+  const float q3 = pow(q, 3);
+  const float neg_q3 = -q3;
+  const float disc = lin2_27 + neg_q3;                // discriminant
+  const float sqrt_disc = sqrt(disc);
+  const float rad = a3 * root3 * sqrt_disc;
+  const float num = term_b + term_x + rad;
+  const float w = inv_a3 * num;                       // the number whose cube root carries the solution
+  const double cbrt_w = pow(w, 1.0 / 3.0);
+  Xarc = (cbrt_w * 0.2403749283845681) / abs_a - b / (a * 2.0) + 1.0 / pow(a, 2) * abs_a * q * 1.0 / pow(w, 1.0 / 3.0) * 0.3466806371753173;
+  Yarc = a * pow(Xarc, 2) + b * Xarc + c;
 }
+
+namespace {
+// (S, rho) of a car-frame point from its foot point on the arc; `tangent_form` selects which of upstream's two (algebraically
+// equal, differently rounded) half-plane expressions decides the sign of rho: the point transform expands the slope, the
+// pose transform uses it as one number
+struct RoadCoords { double S, rho, dydx; };
+RoadCoords roadCoordsOfCarPoint(const std::vector<double>& Cxy, const std::vector<double>& Cxs, double Xcar, double Ycar, double Xarc,
+                                double Yarc, bool tangent_form) {
+  RoadCoords r;
+  r.S = Cxs[0] * pow(Xarc, 2) + Cxs[1] * Xarc + Cxs[2];
+  r.rho = sqrt(pow(Xarc - Xcar, 2) + pow(Yarc - Ycar, 2));
+  r.dydx = 2 * Cxy[0] * Xarc + Cxy[1];
+  const bool below = tangent_form ? (Ycar < (r.dydx * Xcar + Yarc - r.dydx * Xarc))
+                                  : (Ycar < (Yarc - Xarc * (Cxy[1] + 2 * Xarc * Cxy[0]) + Xcar * (Cxy[1] + 2 * Xarc * Cxy[0])));
+  if (below) r.rho = -r.rho;
+  return r;
+}
+// the arc point, slope and signed offset that a point of the straightened road maps back to
+struct ArcCoords { double Xarc, Yarc, dydx, rho; };
+ArcCoords arcCoordsOfRoadPoint(const std::vector<double>& Cxy, const std::vector<double>& Cxs, double Xs, double Ys) {
+  const double Xroads = (Xs - Cxy[2] * Cxy[1] + Cxy[1] * Ys) / (pow(Cxy[1], 2) + 1);
+  const double Yroads = Cxy[2] + (Cxy[1] * (Xs - Cxy[2] * Cxy[1] + Cxy[1] * Ys)) / (pow(Cxy[1], 2) + 1);
+  const double S = sqrt(pow(Xroads, 2) + pow(Yroads - Cxy[2], 2));
+  ArcCoords r;
+  r.rho = sqrt(pow(Xroads - Xs, 2) + pow(Yroads - Ys, 2));
+  if (Ys < (Cxy[1] * Xs + Cxy[2])) r.rho = -r.rho;
+  r.Xarc = -(Cxs[1] - sqrt(pow(Cxs[1], 2) - 4 * Cxs[0] * Cxs[2] + 4 * Cxs[0] * S)) / (2 * Cxs[0]);  // inverse of the arc-length fit
+  r.Yarc = Cxy[0] * pow(r.Xarc, 2) + Cxy[1] * r.Xarc + Cxy[2];
+  r.dydx = 2 * Cxy[0] * r.Xarc + Cxy[1];
+  return r;
+}
+// from the arc point along the road's normal
+void offsetAlongNormal(const ArcCoords& r, double& x, double& y) {
+  const double vx = 1, vy = r.dydx;
+  const double L = sqrt(pow(vx, 2) + pow(vy, 2));
+  const double nx = -(1 / L) * r.dydx, ny = (1 / L);
+  x = r.Xarc + nx * r.rho; y = r.Yarc + ny * r.rho;
+}
+}  // namespace
 
 void RoadFrame::pointCarToRoad(double& Xcar, double& Ycar) const {
   double Xarc, Yarc;
   closestPointOnArc(Xcar, Ycar, Xarc, Yarc);
-  // (S, rho): arc length of the foot point, signed distance from it (sign by the tangent's half-plane)
-  const double S = Cxs_[0] * pow(Xarc, 2) + Cxs_[1] * Xarc + Cxs_[2];
-  double rho = sqrt(pow(Xarc - Xcar, 2) + pow(Yarc - Ycar, 2));
-  if (Ycar < (Yarc - Xarc * (Cxy_[1] + 2 * Xarc * Cxy_[0]) + Xcar * (Cxy_[1] + 2 * Xarc * Cxy_[0]))) rho = -rho;
+  const RoadCoords r = roadCoordsOfCarPoint(Cxy_, Cxs_, Xcar, Ycar, Xarc, Yarc, false);
   const double theta = atan2(Cxy_[1], 1);
-  const double Xstraight = cos(theta) * S - sin(theta) * rho;
-  const double Ystraight = sin(theta) * S + cos(theta) * rho + Cxy_[2];
+  const double Xstraight = cos(theta) * r.S - sin(theta) * r.rho;
+  const double Ystraight = sin(theta) * r.S + cos(theta) * r.rho + Cxy_[2];
   Xcar = Xstraight; Ycar = Ystraight;
 }
 
 void RoadFrame::pointRoadToCar(double& Xstraight, double& Ystraight) const {
-  const std::vector<double>& Cxy = Cxy_;
-  const std::vector<double>& Cxs = Cxs_;
-  // foot point on the straightened road, (S, rho) from it
-  const double Xroads = (Xstraight - Cxy[2] * Cxy[1] + Cxy[1] * Ystraight) / (pow(Cxy[1], 2) + 1);
-  const double Yroads = Cxy[2] + (Cxy[1] * (Xstraight - Cxy[2] * Cxy[1] + Cxy[1] * Ystraight)) / (pow(Cxy[1], 2) + 1);
-  const double S = sqrt(pow(Xroads, 2) + pow(Yroads - Cxy[2], 2));
-  double rho = sqrt(pow(Xroads - Xstraight, 2) + pow(Yroads - Ystraight, 2));
-  if (Ystraight < (Cxy[1] * Xstraight + Cxy[2])) rho = -rho;
-  // back onto the arc: invert the arc-length polynomial, then along the normal
-  const double Xarc = -(Cxs[1] - sqrt(pow(Cxs[1], 2) - 4 * Cxs[0] * Cxs[2] + 4 * Cxs[0] * S)) / (2 * Cxs[0]);
-  const double Yarc = Cxy[0] * pow(Xarc, 2) + Cxy[1] * Xarc + Cxy[2];
-  const double dydx = 2 * Cxy[0] * Xarc + Cxy[1];
-  const double vx = 1, vy = dydx;
-  const double L = sqrt(pow(vx, 2) + pow(vy, 2));
-  const double nx = -(1 / L) * dydx, ny = (1 / L);
-  Xstraight = Xarc + nx * rho; Ystraight = Yarc + ny * rho;
+  offsetAlongNormal(arcCoordsOfRoadPoint(Cxy_, Cxs_, Xstraight, Ystraight), Xstraight, Ystraight);
 }
 
 void RoadFrame::poseCarToRoad(double& Xcar, double& Ycar, double& Hcar) const {
   double Xarc, Yarc;
   closestPointOnArc(Xcar, Ycar, Xarc, Yarc);
-  const double S = Cxs_[0] * pow(Xarc, 2) + Cxs_[1] * Xarc + Cxs_[2];
-  double rho = sqrt(pow(Xarc - Xcar, 2) + pow(Yarc - Ycar, 2));
-  const double dydx = 2 * Cxy_[0] * Xarc + Cxy_[1];
-  if (Ycar < (dydx * Xcar + Yarc - dydx * Xarc)) rho = -rho;
-  const double theta = atan2(Cxy_[1], 1);   // heading of the straightened road
-  const double Hroad = atan2(dydx, 1);      // heading of the road at the foot point
+  const RoadCoords r = roadCoordsOfCarPoint(Cxy_, Cxs_, Xcar, Ycar, Xarc, Yarc, true);
+  const double theta = atan2(Cxy_[1], 1);    // heading of the straightened road
+  const double Hroad = atan2(r.dydx, 1);     // heading of the road at the foot point
   const double Hstraight = wrapTo2Pi((Hcar - Hroad) + theta);
-  const double Xstraight = cos(theta) * S - sin(theta) * rho;
-  const double Ystraight = sin(theta) * S + cos(theta) * rho + Cxy_[2];
+  const double Xstraight = cos(theta) * r.S - sin(theta) * r.rho;
+  const double Ystraight = sin(theta) * r.S + cos(theta) * r.rho + Cxy_[2];
   Xcar = Xstraight; Ycar = Ystraight; Hcar = Hstraight;
 }
 
 void RoadFrame::poseRoadToCar(double& Xstraight, double& Ystraight, double& Hstraight) const {
-  const std::vector<double>& Cxy = Cxy_;
-  const std::vector<double>& Cxs = Cxs_;
-  const double Xroads = (Xstraight - Cxy[2] * Cxy[1] + Cxy[1] * Ystraight) / (pow(Cxy[1], 2) + 1);
-  const double Yroads = Cxy[2] + (Cxy[1] * (Xstraight - Cxy[2] * Cxy[1] + Cxy[1] * Ystraight)) / (pow(Cxy[1], 2) + 1);
-  const double S = sqrt(pow(Xroads, 2) + pow(Yroads - Cxy[2], 2));
-  double rho = sqrt(pow(Xroads - Xstraight, 2) + pow(Yroads - Ystraight, 2));
-  if (Ystraight < (Cxy[1] * Xstraight + Cxy[2])) rho = -rho;
-  const double Xarc = -(Cxs[1] - sqrt(pow(Cxs[1], 2) - 4 * Cxs[0] * Cxs[2] + 4 * Cxs[0] * S)) / (2 * Cxs[0]);
-  const double Yarc = Cxy[0] * pow(Xarc, 2) + Cxy[1] * Xarc + Cxy[2];
-  const double dydx = 2 * Cxy[0] * Xarc + Cxy[1];
-  const double HroadC = atan2(dydx, 1), HroadS = atan2(Cxy[1], 1);
+  const ArcCoords r = arcCoordsOfRoadPoint(Cxy_, Cxs_, Xstraight, Ystraight);
+  const double HroadC = atan2(r.dydx, 1), HroadS = atan2(Cxy_[1], 1);
   const double Hcar = wrapTo2Pi((Hstraight - HroadS) + HroadC);
-  const double vx = 1, vy = dydx;
-  const double L = sqrt(pow(vx, 2) + pow(vy, 2));
-  const double nx = -(1 / L) * dydx, ny = (1 / L);
-  Xstraight = Xarc + nx * rho; Ystraight = Yarc + ny * rho; Hstraight = Hcar;
+  offsetAlongNormal(r, Xstraight, Ystraight);
+  Hstraight = Hcar;
 }
 
 double RoadFrame::steerOfRoadCurvature(double x, double y, const Vehicle& veh) const {
