@@ -299,18 +299,24 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
   float T = INFINITY;   // key and id of the 10th entry (warp-uniform)
   int Tid = INT_MAX;
 
-  // first tile: the first one whose axis interval ends at or after the block's first sample
+  // First tile.  Explore key (Dubins length): the first tile whose axis interval ends at or after the block's first sample,
+  // then outwards in both directions — the best parents are the nearest nodes.  Optimise key (costE + Dubins length): tile 0,
+  // then upwards — the best parents are the nodes near the root, whose cost so far is small (costE + length is about the
+  // straight distance from the root for them, and more for every node off that line), and the root is the origin of the
+  // axis.  The sort keeps the samples of the two keys apart, so a block holds one kind (the one block at the seam takes the
+  // order of its first sample; the order never changes a list, only how early T becomes tight).
   if (threadIdx.x == 0) {
     int lo = 0, hi = so.n_tiles - 1;
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
       if (so.tile_uhi[mid] >= su) hi = mid; else lo = mid + 1;
     }
-    s_start = lo;
+    s_start = optimize ? -1 : lo;
   }
   __syncthreads();
-  const int t0 = s_start;
-  bool open_up = true, open_dn = true;   // block-uniform: directions that may still hold candidates
+  const bool from_root = s_start < 0;
+  const int t0 = from_root ? 0 : s_start;
+  bool open_up = true, open_dn = !from_root;   // block-uniform: directions that may still hold candidates
   for (int step = 0; open_up || open_dn; step++) {
     // visiting order t0, t0+1, t0-1, t0+2, t0-2, ...
     const bool up = (step & 1) != 0 || step == 0;
@@ -328,7 +334,10 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
       const float dv = fmaxf(fmaxf(so.tile_vlo[t] - sv, sv - so.tile_vhi[t]), 0.0f);
       // (dv == 0 for tiles without a lateral interval)
       want = !(0.999f * sqrtf(du * du + dv * dv) + (optimize ? so.tile_ce[t] : 0.0f) > T);
-      axis_open = !(0.999f * du > T);
+      // how far the tile lies BEYOND the sample in the direction of travel: monotone along that direction whatever the
+      // sample's own position is
+      const float da = fmaxf(up ? so.tile_ulo[t] - su : su - so.tile_uhi[t], 0.0f);
+      axis_open = !(0.999f * da > T);
 
     }
     if (!__syncthreads_or(want ? 1 : 0)) {
@@ -354,11 +363,28 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
     __syncthreads();
     if (live && want) {
       // stage 1: distance bound against T, then the float pre-test of feasibility for the nodes that pass it
+      // The nodes of a tile are stored in axis order.  Explore key: they are taken from the sample's own axis position
+      // outwards (tiles before the sample: last node first; the sample's own tile: the part before the sample backwards, then
+      // the rest forwards).  Optimise key: in storage order, root side first.  The list does not depend on the order — it is
+      // ordered by (key, node id) — but its cost does: best first, T is tight after a few insertions and stage 1 drops almost
+      // everything that follows; worst first, every feasible node of the tile is inserted in turn (C3, 4096 nodes, per sample:
+      // 61 -> 13 insertions with the explore key, 104 -> 10 with the optimise key).
+      int split = 0;
+      if (!optimize) {
+        if (so.tile_uhi[t] < su) split = n;
+        else if (!(so.tile_ulo[t] > su)) {
+          for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            split += __popc(__ballot_sync(FULL_MASK, i < n && s_fx[i] * so.cb + s_fy[i] * so.sb < su));
+          }
+        }
+      }
       int c1 = 0;
       for (int i0 = 0; i0 < n; i0 += 32) {
-        const int i = i0 + lane;
+        const int ii = i0 + lane;
+        const int i = ii < split ? split - 1 - ii : ii;
         bool keep = false;
-        if (i < n) keep = stage1_keep(fsx - s_fx[i], fsy - s_fy[i], optimize ? s_ce[i] : 0.0f, T, slack);
+        if (ii < n) keep = stage1_keep(fsx - s_fx[i], fsy - s_fy[i], optimize ? s_ce[i] : 0.0f, T, slack);
         if (keep) keep = feasible_maybe(fsx, fsy, s_frx[i], s_fry[i], s_fdx[i], s_fdy[i], feas_len2);
         const unsigned m = __ballot_sync(FULL_MASK, keep);
         if (keep) s_idx[warp][c1 + __popc(m & lt)] = (uint16_t)i;
