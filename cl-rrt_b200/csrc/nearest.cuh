@@ -42,8 +42,15 @@ struct NearestSorted {
   const float* tile_vlo;    // [n_tiles] lateral interval (infinite for tiles that span more than one axis slab)
   const float* tile_vhi;
   const float* tile_ce;     // [n_tiles] smallest costE in the tile (bound for the optimise key costE + Dubins)
+  const float* tile_proj;   // [n_tiles][NN_DIRS] projected cost bound of the tile (nn_tile_kernel)
   const int32_t* sample_id; // [K] original index of the sample at a sorted position
   float cb, sb;             // axis direction
+  // where the search of an explore sample starts (see nearest_sorted_kernel): the bin grid of the sort and the mean axis
+  // offset from a node to the end of its own reference
+  const int32_t* bin_end;   // [NN_BINS] sorted position after the last node of every bin
+  const float* lead_sum;    // sum over the nodes of (reference end - position) . axis
+  float u0, inv_bin, v0, inv_vbin;
+  int32_t nl_log2;
 };
 
 struct NearestArgs {
@@ -77,6 +84,7 @@ struct NNSortArgs {
   float *fx, *fy, *frx, *fry, *fdx, *fdy;
   int32_t* sbin;       // [n_nodes] bin of the node at a sorted position
   int32_t* sample_id;
+  float* lead_sum;     // hist + 3 * NN_BINS (zeroed with it)
 };
 
 __device__ __forceinline__ int nn_bin_of(float u, float u0, float inv_bin, int nbins) {
@@ -87,9 +95,13 @@ __device__ __forceinline__ int nn_bin_of(float u, float u0, float inv_bin, int n
 __global__ void __launch_bounds__(256) nn_bin_kernel(const NNSortArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int key = -1;
+  float lead = 0.0f;
   if (i < a.n_nodes + a.K) {
     float x, y;
-    if (i < a.n_nodes) { x = (float)a.tree.x[i]; y = (float)a.tree.y[i]; }
+    if (i < a.n_nodes) {
+      x = (float)a.tree.x[i]; y = (float)a.tree.y[i];
+      lead = ((float)a.tree.rbx[i] - x) * a.cb + ((float)a.tree.rby[i] - y) * a.sb;
+    }
     else { x = (float)a.sample_xy[2 * (i - a.n_nodes)]; y = (float)a.sample_xy[2 * (i - a.n_nodes) + 1]; }
     const float u = x * a.cb + y * a.sb, v = y * a.cb - x * a.sb;
     int b = (nn_bin_of(u, a.u0, a.inv_bin, NN_BINS >> a.nl_log2) << a.nl_log2) | nn_bin_of(v, a.v0, a.inv_vbin, 1 << a.nl_log2);
@@ -99,6 +111,10 @@ __global__ void __launch_bounds__(256) nn_bin_kernel(const NNSortArgs a) {
   }
   const unsigned peers = __match_any_sync(FULL_MASK, key);
   if (key >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&a.hist[key], __popc(peers));
+  if (blockIdx.x * blockDim.x < a.n_nodes) {  // (block-uniform) a hint only: the order of the additions does not matter
+    for (int o = 16; o > 0; o >>= 1) lead += __shfl_xor_sync(FULL_MASK, lead, o);
+    if ((threadIdx.x & 31) == 0 && lead != 0.0f) atomicAdd(a.lead_sum, lead);
+  }
 }
 
 // exclusive scans of the histograms (block 0: the NN_BINS node bins, block 1: the 2 * NN_BINS sample bins, two per thread)
@@ -150,20 +166,54 @@ __global__ void __launch_bounds__(256) nn_scatter_kernel(const NNSortArgs a) {
 
 // Per tile: the axis interval, from the BIN edges of its first and last node (the nodes are sorted by bin, not by
 // coordinate: monotone along the tile order by construction; the end bins also hold everything outside the binned
-// range, so their outer edges are infinite; 1 cm of slack covers the float rounding of the bin assignment), and the
-// smallest costE (NaN-safe: a tile with a NaN cost reports -inf and is never skipped).
+// range, so their outer edges are infinite; 1 cm of slack covers the float rounding of the bin assignment), the
+// smallest costE (NaN-safe: a tile with a NaN cost reports -inf and is never skipped), and the PROJECTED bound of the
+// optimise key: for any unit vector e,  costE + Dubins(N -> S) >= costE + 0.999 |S - N| >= (costE - 0.999 N.e) + 0.999 S.e,
+// so  proj[t][k] = min over the tile of (costE - 0.999 N.e_k)  bounds every key of the tile from below for a sample S by
+// proj[t][k] + 0.999 S.e_k — for each direction e_k of a fan of NN_DIRS around the axis, the best of which is the one
+// closest to the bearing of S from the tile.  costE is the length driven from the root, so on a dense tree the 10th best
+// optimise key of a sample is its straight distance from the root to within millimetres, and the box bound (distance to
+// the tile's box + the tile's smallest costE) is loose by the size of the box in every tile near that line; the projected
+// bound keeps the correlation between cost and position inside the tile (2.3e5 nodes: 321 -> 47 tiles per sample).
+#define NN_DIRS 9  // -40 .. 40 degrees from the axis
+__device__ __forceinline__ void nn_dir(int k, float* c, float* s) {
+  const float a = (float)(k - NN_DIRS / 2) * 0.17453293f;
+  *c = cosf(a); *s = sinf(a);
+}
 __global__ void __launch_bounds__(NEAREST_TILE) nn_tile_kernel(const int32_t* __restrict__ sbin, const float* __restrict__ ce,
+                                                                const float* __restrict__ fx, const float* __restrict__ fy,
+                                                                float cb, float sb,
                                                                 int n_nodes, float u0, float bin_w, float v0, float vbin_w,
                                                                 int nl_log2, float* __restrict__ ulo, float* __restrict__ uhi,
                                                                 float* __restrict__ vlo, float* __restrict__ vhi,
-                                                                float* __restrict__ cemin) {
+                                                                float* __restrict__ cemin, float* __restrict__ proj) {
   __shared__ float smn[NEAREST_TILE / 32];
+  __shared__ float spr[NEAREST_TILE / 32][NN_DIRS];
   const int t = blockIdx.x, i = t * NEAREST_TILE + threadIdx.x;
   float mn = INFINITY;
-  if (i < n_nodes) { const float c = ce[i]; mn = c == c ? c : -INFINITY; }
+  float c = 0.0f, u = 0.0f, v = 0.0f;
+  if (i < n_nodes) {
+    c = ce[i]; mn = c == c ? c : -INFINITY;
+    const float x = fx[i], y = fy[i];
+    u = x * cb + y * sb; v = y * cb - x * sb;
+  }
   for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(FULL_MASK, mn, o));
   if ((threadIdx.x & 31) == 0) smn[threadIdx.x >> 5] = mn;
+  for (int k = 0; k < NN_DIRS; k++) {
+    float dc, ds;
+    nn_dir(k, &dc, &ds);
+    float g = INFINITY;
+    if (i < n_nodes) { g = c - 0.999f * (u * dc + v * ds); if (!(g == g)) g = -INFINITY; }
+    for (int o = 16; o > 0; o >>= 1) g = fminf(g, __shfl_xor_sync(FULL_MASK, g, o));
+    if ((threadIdx.x & 31) == 0) spr[threadIdx.x >> 5][k] = g;
+  }
   __syncthreads();
+  if (threadIdx.x < NN_DIRS) {
+    float g = spr[0][threadIdx.x];
+    for (int w = 1; w < NEAREST_TILE / 32; w++) g = fminf(g, spr[w][threadIdx.x]);
+    // the float rounding of the node's side of the bound (products of magnitudes up to |g| + |N|) is taken off here
+    proj[(size_t)t * NN_DIRS + threadIdx.x] = g - (1.0e-3f + 1.0e-5f * fabsf(g));
+  }
   if (threadIdx.x == 0) {
     for (int w = 1; w < NEAREST_TILE / 32; w++) mn = fminf(mn, smn[w]);
     const int b0 = sbin[t * NEAREST_TILE], b1 = sbin[min(t * NEAREST_TILE + NEAREST_TILE - 1, n_nodes - 1)];
@@ -269,6 +319,12 @@ __device__ __forceinline__ bool feasible_maybe(float fsx, float fsy, float frx, 
 // even loaded, when its axis interval is that far from all 8 samples of the block (tiles are visited from the samples'
 // own position outwards, so T is tight after the first tile or two).  Three compaction stages keep the expensive
 // parts on full warps: distance bound (all nodes of a tile) -> feasibility (survivors) -> key (feasible survivors).
+#ifdef CLRRT_NN_STATS  // diagnostic build (scripts/build_variant.sh): what the search spends its time on
+__device__ unsigned long long g_nn_stats[8];  // tile steps, tiles loaded, warp-tiles searched, stage-1 survivors, feasible, inserted, explore/optimise samples
+#define NN_STAT(k, v) atomicAdd(&g_nn_stats[k], (unsigned long long)(v))
+#else
+#define NN_STAT(k, v)
+#endif
 __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const NearestArgs a) {
   // a tile stages seven floats per node (position, reference end, reference direction, costE): all that the distance bound
   // and the feasibility pre-test read; the double fields of the few survivors come straight from the sorted arrays
@@ -277,10 +333,13 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
   __shared__ uint16_t s_idx[NEAREST_WARPS][NEAREST_TILE];
   __shared__ uint16_t s_idx2[NEAREST_WARPS][NEAREST_TILE];
   __shared__ int s_start;
+  __shared__ unsigned s_mask[3][2];   // per chunk of 32 tiles: wanted by any sample / axis-open for any sample (3 in rotation)
   const NearestSorted& so = a.so;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
-  const int js = blockIdx.x * NEAREST_WARPS + warp;   // position in the sorted sample order
+  // position in the sorted sample order; last blocks first: the optimise-key samples are sorted after the explore-key ones
+  // and take about three times as long each, so they are started first and the short blocks fill in behind them
+  const int js = (gridDim.x - 1 - blockIdx.x) * NEAREST_WARPS + warp;
   const bool live = js < a.K;
   const int j = live ? so.sample_id[js] : 0;
   double sx = 0, sy = 0;
@@ -294,66 +353,102 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
   const float fsx = (float)sx, fsy = (float)sy;
   const float slack = 1.0e-3f + 4.0e-7f * (fabsf(fsx) + fabsf(fsy));
   const float feas_len2 = (float)(a.feas_len * a.feas_len);
+  // optimise key: 0.999 (sample . e_k) for direction k = lane of the fan, and the float rounding of the whole bound
+  float proj_s = 0.0f;
+  if (lane < NN_DIRS) { float c, sn; nn_dir(lane, &c, &sn); proj_s = 0.999f * (su * c + sv * sn); }
+  const float proj_tol = 2.0e-3f + 1.0e-5f * (fabsf(su) + fabsf(sv));
   float lk = INFINITY;  // entry `lane` of the list (lanes >= 10 stay at +inf / INT_MAX and never take part)
   int lid = INT_MAX;
   float T = INFINITY;   // key and id of the 10th entry (warp-uniform)
   int Tid = INT_MAX;
 
-  // First tile.  Explore key (Dubins length): the first tile whose axis interval ends at or after the block's first sample,
-  // then outwards in both directions — the best parents are the nearest nodes.  Optimise key (costE + Dubins length): tile 0,
-  // then upwards — the best parents are the nodes near the root, whose cost so far is small (costE + length is about the
-  // straight distance from the root for them, and more for every node off that line), and the root is the origin of the
-  // axis.  The sort keeps the samples of the two keys apart, so a block holds one kind (the one block at the seam takes the
-  // order of its first sample; the order never changes a list, only how early T becomes tight).
+  // First tile.  Explore key (Dubins length): a feasible parent is a node whose own reference ends just before the sample
+  // (feasibleNode, rrtplanner.cpp:271-289) — and a node stops about one look-ahead distance short of the end of its
+  // reference, so the best parents lie that far BEHIND the sample, not around it.  The search starts at the tile of the bin
+  // (axis position - mean lead of the tree's nodes, lateral position of the sample) and goes outwards in both directions;
+  // started at the sample's own position it scanned some 200 tiles of infeasible nodes with T still infinite (2.3e5 nodes).
+  // Optimise key (costE + Dubins length): tile 0, then upwards — the best parents are the nodes near the root, whose cost so
+  // far is small (costE + length is about the straight distance from the root for them, and more for every node off that
+  // line), and the root is the origin of the axis.  The sort keeps the samples of the two keys apart, so a block holds one
+  // kind (the one block at the seam takes the order of its first sample).  Any start gives the same lists: the order never
+  // changes a list, only how early T becomes tight.
   if (threadIdx.x == 0) {
-    int lo = 0, hi = so.n_tiles - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (so.tile_uhi[mid] >= su) hi = mid; else lo = mid + 1;
+    int start = -1;
+    if (!optimize) {
+      const float lead = *so.lead_sum / (float)so.n_nodes;
+      const float us = su - (fabsf(lead) < 1.0e6f ? lead : 0.0f);
+      const int b = (nn_bin_of(us, so.u0, so.inv_bin, NN_BINS >> so.nl_log2) << so.nl_log2) |
+                    nn_bin_of(sv, so.v0, so.inv_vbin, 1 << so.nl_log2);
+      const int first = b > 0 ? so.bin_end[b - 1] : 0;
+      start = min(max(first, 0) / NEAREST_TILE, so.n_tiles - 1);
     }
-    s_start = optimize ? -1 : lo;
+    s_start = start;
+    for (int k = 0; k < 3; k++) { s_mask[k][0] = 0; s_mask[k][1] = 0; }
   }
   __syncthreads();
   const bool from_root = s_start < 0;
   const int t0 = from_root ? 0 : s_start;
+  // Tiles are voted on 32 at a time: lane i of every warp computes the lower bound `lb` of its sample's keys over tile i of
+  // the chunk (box bound; for the optimise key also the projected bound), one ballot per warp and one OR over the block
+  // give the tiles that ANY sample of the block still needs, and only those are loaded.  (One tile per vote cost two block
+  // barriers and some 100 instructions per warp and tile — 740 of them per block at 2.3e5 nodes, nine in ten for a tile
+  // nobody needed.)  Chunks alternate between the two directions, nearest chunk first; a direction is finished when the
+  // farthest tile of its chunk is beyond T along the axis for every sample (axis intervals are monotone along the tile order
+  // and T only shrinks) or the tiles run out.
+  float proj_all[NN_DIRS];
+#pragma unroll
+  for (int k = 0; k < NN_DIRS; k++) proj_all[k] = __shfl_sync(FULL_MASK, proj_s, k);
   bool open_up = true, open_dn = !from_root;   // block-uniform: directions that may still hold candidates
-  for (int step = 0; open_up || open_dn; step++) {
-    // visiting order t0, t0+1, t0-1, t0+2, t0-2, ...
-    const bool up = (step & 1) != 0 || step == 0;
-    const int off = (step + 1) >> 1;
-    const int t = up ? t0 + off : t0 - off;
-    if (up && !open_up) continue;
-    if (!up && !open_dn) continue;
-    if (t < 0) { open_dn = false; continue; }
-    if (t >= so.n_tiles) { open_up = false; continue; }
-    // does any sample of the block still need this tile?  axis distance <= Euclidean distance <= key / 0.999 (+ the
-    // tile's smallest costE for the optimise key)
-    bool want = false, axis_open = false;
-    if (live) {
-      const float du = fmaxf(fmaxf(so.tile_ulo[t] - su, su - so.tile_uhi[t]), 0.0f);
-      const float dv = fmaxf(fmaxf(so.tile_vlo[t] - sv, sv - so.tile_vhi[t]), 0.0f);
+  int cu = 0, cd = 0;                          // chunks done in each direction
+  for (int chunk = 0; open_up || open_dn; chunk++) {
+    const bool up = open_up && (!open_dn || cu <= cd);
+    const int first = up ? t0 + 32 * cu : t0 - 1 - 32 * cd;   // tile of lane 0; lanes go outwards
+    if (up) cu++; else cd++;
+    const int tl = up ? first + lane : first - lane;
+    float lb = INFINITY;
+    bool axis_open = false;
+    if (live && tl >= 0 && tl < so.n_tiles) {
+      // axis distance <= Euclidean distance <= key / 0.999 (+ the tile's smallest costE for the optimise key)
+      const float ulo = so.tile_ulo[tl], uhi = so.tile_uhi[tl];
+      const float du = fmaxf(fmaxf(ulo - su, su - uhi), 0.0f);
+      const float dv = fmaxf(fmaxf(so.tile_vlo[tl] - sv, sv - so.tile_vhi[tl]), 0.0f);
       // (dv == 0 for tiles without a lateral interval)
-      want = !(0.999f * sqrtf(du * du + dv * dv) + (optimize ? so.tile_ce[t] : 0.0f) > T);
-      // how far the tile lies BEYOND the sample in the direction of travel: monotone along that direction whatever the
-      // sample's own position is
-      const float da = fmaxf(up ? so.tile_ulo[t] - su : su - so.tile_uhi[t], 0.0f);
-      axis_open = !(0.999f * da > T);
-
-    }
-    if (!__syncthreads_or(want ? 1 : 0)) {
-      // Nobody needs this tile: it is skipped.  The DIRECTION is finished only when the axis distance alone rules the tile
-      // out for every sample: the axis intervals are monotone along the tile order and T only shrinks, so every tile
-      // farther out is ruled out too.  (The lateral interval and the tile's smallest costE are not monotone along the
-      // order — the root, 30 m behind a sample, is the best parent by the optimise key — so they only skip.)
-      if (!__syncthreads_or(axis_open ? 1 : 0)) {
-        if (step == 0) { open_up = false; open_dn = false; }  // (cannot happen while a list is still open: T is infinite)
-        else if (up) open_up = false;
-        else open_dn = false;
+      lb = 0.999f * sqrtf(du * du + dv * dv);
+      if (optimize) {
+        lb += so.tile_ce[tl];
+        // projected bound of the optimise key (nn_tile_kernel), the best direction of the fan
+        const float* pr = so.tile_proj + (size_t)tl * NN_DIRS;
+        float bnd = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < NN_DIRS; k++) bnd = fmaxf(bnd, pr[k] + proj_all[k]);
+        lb = fmaxf(lb, bnd - proj_tol);   // (fmaxf drops a NaN operand: the other bound stands)
       }
-      continue;
+      // how far the tile lies BEYOND the sample in the direction of travel: monotone along that direction whatever the
+      // sample's own position is.  (The lateral interval and the costs are not monotone along the order — the root, 30 m
+      // behind a sample, is the best parent by the optimise key — so they only skip tiles, they never end a direction.)
+      const float da = fmaxf(up ? ulo - su : su - uhi, 0.0f);
+      axis_open = !(0.999f * da > T);
     }
+    const unsigned wm = __ballot_sync(FULL_MASK, live && tl >= 0 && tl < so.n_tiles && !(lb > T));
+    const unsigned om = __ballot_sync(FULL_MASK, axis_open);
+    unsigned* mk = s_mask[chunk % 3];
+    if (lane == 0) { if (wm) atomicOr(&mk[0], wm); if (om) atomicOr(&mk[1], om); }
+    __syncthreads();
+    unsigned want_any = mk[0];
+    const unsigned open_any = mk[1];
+    if (threadIdx.x == 0) { s_mask[(chunk + 2) % 3][0] = 0; s_mask[(chunk + 2) % 3][1] = 0; NN_STAT(0, 1); }
+    if (!(open_any >> 31)) { if (up) open_up = false; else open_dn = false; }
+    while (want_any) {
+    const int bit = __ffs(want_any) - 1;
+    want_any &= want_any - 1;
+    const int t = up ? first + bit : first - bit;
+    const bool want = live && !(__shfl_sync(FULL_MASK, lb, bit) > T) && ((wm >> bit) & 1u);
+    // T has moved since the chunk was voted on: is the tile still needed?  (This barrier also separates the reads of the
+    // previous tile from the loads of this one.)
+    if (!__syncthreads_or(want ? 1 : 0)) continue;
     const int base = t * NEAREST_TILE;
     const int n = min(NEAREST_TILE, so.n_nodes - base);
+    if (threadIdx.x == 0) NN_STAT(1, 1);
     if ((int)threadIdx.x < n) {
       const int g = base + threadIdx.x;
       s_fx[threadIdx.x] = so.fx[g]; s_fy[threadIdx.x] = so.fy[g]; s_ce[threadIdx.x] = so.ce[g];
@@ -361,7 +456,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
       s_fdx[threadIdx.x] = so.fdx[g]; s_fdy[threadIdx.x] = so.fdy[g];
     }
     __syncthreads();
-    if (live && want) {
+    if (want) {
       // stage 1: distance bound against T, then the float pre-test of feasibility for the nodes that pass it
       // The nodes of a tile are stored in axis order.  Explore key: they are taken from the sample's own axis position
       // outwards (tiles before the sample: last node first; the sample's own tile: the part before the sample backwards, then
@@ -391,6 +486,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
         c1 += __popc(m);
       }
       __syncwarp();
+      if (lane == 0) { NN_STAT(2, 1); NN_STAT(3, c1); }
       // stage 2: feasibility of the survivors, in the reference's double arithmetic
       int c2 = 0;
       for (int q0 = 0; q0 < c1; q0 += 32) {
@@ -407,6 +503,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
         c2 += __popc(m);
       }
       __syncwarp();
+      if (lane == 0) NN_STAT(4, c2);
       // stage 3: Dubins keys of the feasible survivors and insertion into the warp's list
       for (int q0 = 0; q0 < c2; q0 += 32) {
         const int q = q0 + lane;
@@ -426,6 +523,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
           const float nk = __shfl_sync(FULL_MASK, key, src);
           const int nid = __shfl_sync(FULL_MASK, idx, src);
           if (!(nk < T || (nk == T && nid < Tid))) continue;  // T moved since the ballot
+          if (lane == 0) NN_STAT(5, 1);
           // position = number of entries ordered before the new one; entries from there on move down one lane
           const bool before = lk < nk || (lk == nk && lid < nid);
           const int pos = __popc(__ballot_sync(FULL_MASK, before && lane < CLRRT_SORT_LIMIT));
@@ -441,9 +539,10 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
       }
       __syncwarp();
     }
-    __syncthreads();
+    }
   }
   if (!live) return;
+  if (lane == 0) NN_STAT(optimize ? 7 : 6, 1);
   const int cnt = __popc(__ballot_sync(FULL_MASK, lane < CLRRT_SORT_LIMIT && lid != INT_MAX));
   if (lane < CLRRT_SORT_LIMIT) {
     const bool valid = lid != INT_MAX;
