@@ -70,7 +70,7 @@ struct clrrt_ctx {
   // candidate search: nodes and samples sorted along the goal bearing (nearest.cuh)
   void* nn_mem = nullptr;
   NNSortArgs nn{};
-  float *d_tile_ulo = nullptr, *d_tile_uhi = nullptr, *d_tile_vlo = nullptr, *d_tile_vhi = nullptr, *d_tile_ce = nullptr, *d_tile_proj = nullptr;
+  float *d_tile_ulo = nullptr, *d_tile_uhi = nullptr, *d_tile_vlo = nullptr, *d_tile_vhi = nullptr, *d_tile_ce = nullptr, *d_tile_proj = nullptr, *d_tile_feas = nullptr;
   NodeRecord* d_export = nullptr;    // staging of clrrt_tree_download_range
   size_t export_cap = 0;
   cudaStream_t copy_stream = nullptr;   // clrrt_tree_download_range_async: device-to-host copies beside the next round
@@ -332,7 +332,7 @@ int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_r
   ok &= mal((void**)&ctx->d_bucket, K * CLRRT_SORT_LIMIT);
   {
     const size_t n8 = ((size_t)tree_capacity + 7) & ~(size_t)7, k8 = (K + 7) & ~(size_t)7;
-    const size_t bytes = n8 * (7 * 8 + 9 * 4 + 4 + 4) + (n8 + k8) * 4 + k8 * 4 + 3 * NN_BINS * 4 + (8 + NN_DIRS) * (n8 / NEAREST_TILE + 8) * 4 + 2048;
+    const size_t bytes = n8 * (7 * 8 + 9 * 4 + 4 + 4) + (n8 + k8) * 4 + k8 * 4 + (NN_HIST_INTS + 4) * 4 + (8 + NN_DIRS + NN_FCLS) * (n8 / NEAREST_TILE + 8) * 4 + 2048;
     ok &= mal(&ctx->nn_mem, bytes);
     if (ok) {
       unsigned char* p = reinterpret_cast<unsigned char*>(ctx->nn_mem);
@@ -346,14 +346,15 @@ int clrrt_create(const clrrt_params* p, int device, int tree_capacity, int max_r
       s.sbin = reinterpret_cast<int32_t*>(take(n8 * 4));
       s.bin = reinterpret_cast<int32_t*>(take((n8 + k8) * 4));
       s.sample_id = reinterpret_cast<int32_t*>(take(k8 * 4));
-      s.hist = reinterpret_cast<int32_t*>(take((3 * NN_BINS + 4) * 4));
-      s.lead_sum = reinterpret_cast<float*>(s.hist + 3 * NN_BINS);
+      s.hist = reinterpret_cast<int32_t*>(take((NN_HIST_INTS + 4) * 4));
+      s.lead_sum = reinterpret_cast<float*>(s.hist + NN_HIST_INTS);
       ctx->d_tile_ce = reinterpret_cast<float*>(take((n8 / NEAREST_TILE + 8) * 4));
       ctx->d_tile_ulo = reinterpret_cast<float*>(take((n8 / NEAREST_TILE + 8) * 4));
       ctx->d_tile_uhi = reinterpret_cast<float*>(take((n8 / NEAREST_TILE + 8) * 4));
       ctx->d_tile_vlo = reinterpret_cast<float*>(take((n8 / NEAREST_TILE + 8) * 4));
       ctx->d_tile_vhi = reinterpret_cast<float*>(take((n8 / NEAREST_TILE + 8) * 4));
       ctx->d_tile_proj = reinterpret_cast<float*>(take((n8 / NEAREST_TILE + 8) * NN_DIRS * 4));
+      ctx->d_tile_feas = reinterpret_cast<float*>(take((n8 / NEAREST_TILE + 8) * NN_FCLS * 4));
     }
   }
   ctx->init_stride = ((K * CLRRT_SORT_LIMIT + (size_t)ctx->num_sms * ROLLOUT_MAX_THREADS_PER_SM) + 31) & ~(size_t)31;
@@ -855,12 +856,12 @@ static int nearest_dev(clrrt_ctx* ctx, const double* d_samples, const uint8_t* d
   const float vbin_w = 16.0f / (float)(1 << s.nl_log2);
   s.inv_vbin = 1.0f / vbin_w;
   const int n_el = ctx->n_tree + K, n_tiles = (ctx->n_tree + NEAREST_TILE - 1) / NEAREST_TILE;
-  CK(cudaMemsetAsync(s.hist, 0, (3 * NN_BINS + 4) * sizeof(int32_t), st));
+  CK(cudaMemsetAsync(s.hist, 0, (NN_HIST_INTS + 4) * sizeof(int32_t), st));
   nn_bin_kernel<<<(n_el + 255) / 256, 256, 0, st>>>(s);
   nn_scan_kernel<<<2, NN_BINS, 0, st>>>(s.hist);
   nn_scatter_kernel<<<(n_el + 255) / 256, 256, 0, st>>>(s);
-  nn_tile_kernel<<<n_tiles, NEAREST_TILE, 0, st>>>(s.sbin, s.ce, s.fx, s.fy, s.cb, s.sb, ctx->n_tree, s.u0, bin_w, s.v0, vbin_w, s.nl_log2, ctx->d_tile_ulo,
-                                                   ctx->d_tile_uhi, ctx->d_tile_vlo, ctx->d_tile_vhi, ctx->d_tile_ce, ctx->d_tile_proj);
+  nn_tile_kernel<<<n_tiles, NEAREST_TILE, 0, st>>>(s.sbin, s.ce, s.fx, s.fy, s.frx, s.fry, s.fdx, s.fdy, s.cb, s.sb, ctx->n_tree, s.u0, bin_w, s.v0, vbin_w, s.nl_log2, ctx->d_tile_ulo,
+                                                   ctx->d_tile_uhi, ctx->d_tile_vlo, ctx->d_tile_vhi, ctx->d_tile_ce, ctx->d_tile_proj, ctx->d_tile_feas);
   CK(cudaGetLastError());
   // 2. the search
   NearestArgs a;
@@ -870,7 +871,7 @@ static int nearest_dev(clrrt_ctx* ctx, const double* d_samples, const uint8_t* d
   a.so.nx = s.nx; a.so.ny = s.ny; a.so.rbx = s.rbx; a.so.rby = s.rby; a.so.dpx = s.dpx; a.so.dpy = s.dpy; a.so.ang = s.ang;
   a.so.ca = s.ca; a.so.sa = s.sa; a.so.ce = s.ce;
   a.so.fx = s.fx; a.so.fy = s.fy; a.so.frx = s.frx; a.so.fry = s.fry; a.so.fdx = s.fdx; a.so.fdy = s.fdy;
-  a.so.tile_ulo = ctx->d_tile_ulo; a.so.tile_uhi = ctx->d_tile_uhi; a.so.tile_vlo = ctx->d_tile_vlo; a.so.tile_vhi = ctx->d_tile_vhi; a.so.tile_ce = ctx->d_tile_ce; a.so.tile_proj = ctx->d_tile_proj;
+  a.so.tile_ulo = ctx->d_tile_ulo; a.so.tile_uhi = ctx->d_tile_uhi; a.so.tile_vlo = ctx->d_tile_vlo; a.so.tile_vhi = ctx->d_tile_vhi; a.so.tile_ce = ctx->d_tile_ce; a.so.tile_proj = ctx->d_tile_proj; a.so.tile_feas = ctx->d_tile_feas;
   a.so.sample_id = s.sample_id; a.so.cb = s.cb; a.so.sb = s.sb;
   a.so.bin_end = s.hist; a.so.lead_sum = s.lead_sum; a.so.u0 = s.u0; a.so.inv_bin = s.inv_bin; a.so.v0 = s.v0; a.so.inv_vbin = s.inv_vbin;
   a.so.nl_log2 = s.nl_log2;

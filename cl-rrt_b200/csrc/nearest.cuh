@@ -19,7 +19,22 @@
 #define NEAREST_THREADS (NEAREST_WARPS * 32)
 #define NEAREST_TILE 256
 
-#define NN_BINS 1024  // bins of the sort axis (projection on the goal bearing)
+#define NN_BINS 1024  // spatial bins of the sort (axis slab x lateral bin; the axis is the goal bearing)
+// Inside a spatial bin the nodes are ordered by the DIRECTION CLASS of their own reference (angle of dp = rb - rf from the
+// axis, NN_FCLS classes of 22.5 degrees), so that a tile of a large tree holds one or a few classes: that is what makes
+// the feasibility bound of a tile (nn_tile_kernel) effective.  Node bin = spatial bin * NN_FCLS + class.
+#define NN_FCLS 16
+#define NN_NODE_BINS (NN_BINS * NN_FCLS)
+#define NN_HIST_INTS (NN_NODE_BINS + 2 * NN_BINS)   // node bins; samples with the explore key; samples with the optimise key
+__constant__ float2 c_nn_fdir[NN_FCLS] = {   // centre direction of class c: angle -pi + (c + 0.5) 2 pi / 16
+    {-0.98078528f, -0.195090322f}, {-0.831469612f, -0.555570233f}, {-0.555570233f, -0.831469612f}, {-0.195090322f, -0.98078528f},
+    {0.195090322f, -0.98078528f},  {0.555570233f, -0.831469612f},  {0.831469612f, -0.555570233f},  {0.98078528f, -0.195090322f},
+    {0.98078528f, 0.195090322f},   {0.831469612f, 0.555570233f},   {0.555570233f, 0.831469612f},   {0.195090322f, 0.98078528f},
+    {-0.195090322f, 0.98078528f},  {-0.555570233f, 0.831469612f},  {-0.831469612f, 0.555570233f},  {-0.98078528f, 0.195090322f}};
+__device__ __forceinline__ int nn_dir_class(float dpu, float dpv) {
+  const float th = atan2f(dpv, dpu);
+  return th == th ? min(max((int)((th + 3.14159265f) * (NN_FCLS / 6.28318531f)), 0), NN_FCLS - 1) : 0;
+}
 // the sort pays off from about 1e8 (sample, node) pairs per call (measured: C3 2.7e8 pairs 1.59 -> 1.15 ms; 4096 x 4096
 // 0.15 -> 0.26 ms); below, all tiles are searched in storage order
 #define NN_SORT_MIN_PAIRS 1.0e8
@@ -43,11 +58,12 @@ struct NearestSorted {
   const float* tile_vhi;
   const float* tile_ce;     // [n_tiles] smallest costE in the tile (bound for the optimise key costE + Dubins)
   const float* tile_proj;   // [n_tiles][NN_DIRS] projected cost bound of the tile (nn_tile_kernel)
+  const float* tile_feas;   // [n_tiles][NN_FCLS] feasibility bound of the tile (nn_tile_kernel)
   const int32_t* sample_id; // [K] original index of the sample at a sorted position
   float cb, sb;             // axis direction
   // where the search of an explore sample starts (see nearest_sorted_kernel): the bin grid of the sort and the mean axis
   // offset from a node to the end of its own reference
-  const int32_t* bin_end;   // [NN_BINS] sorted position after the last node of every bin
+  const int32_t* bin_end;   // [NN_NODE_BINS] sorted position after the last node of every node bin
   const float* lead_sum;    // sum over the nodes of (reference end - position) . axis
   float u0, inv_bin, v0, inv_vbin;
   int32_t nl_log2;
@@ -75,7 +91,7 @@ struct NNSortArgs {
   float v0, inv_vbin;          // lateral coordinate v = -x sb + y cb: 1 << nl_log2 bins from v0
   int32_t nl_log2;             // bin = slab << nl_log2 | lateral bin (0: axis only)
   int32_t* bin;        // [n_nodes + K] bin of every element (nodes first)
-  int32_t* hist;       // [3 * NN_BINS]: nodes; samples with the explore key; samples with the optimise key (so that the 8
+  int32_t* hist;       // [NN_HIST_INTS]: nodes; samples with the explore key; samples with the optimise key (so that the 8
                        // samples of a block share a heuristic: the two keys prune very differently)
   // outputs of the scatter
   int32_t* node_id;
@@ -84,7 +100,7 @@ struct NNSortArgs {
   float *fx, *fy, *frx, *fry, *fdx, *fdy;
   int32_t* sbin;       // [n_nodes] bin of the node at a sorted position
   int32_t* sample_id;
-  float* lead_sum;     // hist + 3 * NN_BINS (zeroed with it)
+  float* lead_sum;     // hist + NN_HIST_INTS (zeroed with it)
 };
 
 __device__ __forceinline__ int nn_bin_of(float u, float u0, float inv_bin, int nbins) {
@@ -98,16 +114,21 @@ __global__ void __launch_bounds__(256) nn_bin_kernel(const NNSortArgs a) {
   float lead = 0.0f;
   if (i < a.n_nodes + a.K) {
     float x, y;
+    int cls = 0;
     if (i < a.n_nodes) {
       x = (float)a.tree.x[i]; y = (float)a.tree.y[i];
-      lead = ((float)a.tree.rbx[i] - x) * a.cb + ((float)a.tree.rby[i] - y) * a.sb;
+      const double rbx = a.tree.rbx[i], rby = a.tree.rby[i];
+      lead = ((float)rbx - x) * a.cb + ((float)rby - y) * a.sb;
+      const float dx = (float)(rbx - a.tree.rfx[i]), dy = (float)(rby - a.tree.rfy[i]);
+      cls = nn_dir_class(dx * a.cb + dy * a.sb, dy * a.cb - dx * a.sb);
     }
     else { x = (float)a.sample_xy[2 * (i - a.n_nodes)]; y = (float)a.sample_xy[2 * (i - a.n_nodes) + 1]; }
     const float u = x * a.cb + y * a.sb, v = y * a.cb - x * a.sb;
     int b = (nn_bin_of(u, a.u0, a.inv_bin, NN_BINS >> a.nl_log2) << a.nl_log2) | nn_bin_of(v, a.v0, a.inv_vbin, 1 << a.nl_log2);
-    if (i >= a.n_nodes && a.heuristic[i - a.n_nodes]) b += NN_BINS;
+    if (i < a.n_nodes) b = b * NN_FCLS + cls;
+    else if (a.heuristic[i - a.n_nodes]) b += NN_BINS;
     a.bin[i] = b;
-    key = (i < a.n_nodes ? 0 : NN_BINS) + b;
+    key = (i < a.n_nodes ? 0 : NN_NODE_BINS) + b;
   }
   const unsigned peers = __match_any_sync(FULL_MASK, key);
   if (key >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&a.hist[key], __popc(peers));
@@ -117,14 +138,18 @@ __global__ void __launch_bounds__(256) nn_bin_kernel(const NNSortArgs a) {
   }
 }
 
-// exclusive scans of the histograms (block 0: the NN_BINS node bins, block 1: the 2 * NN_BINS sample bins, two per thread)
+// exclusive scans of the histograms (block 0: the NN_NODE_BINS node bins, 16 consecutive bins per thread; block 1: the
+// 2 * NN_BINS sample bins, two per thread)
 __global__ void __launch_bounds__(NN_BINS) nn_scan_kernel(int32_t* __restrict__ hist) {
   __shared__ int32_t s[NN_BINS];
-  const int per = blockIdx.x == 0 ? 1 : 2;
-  int32_t* h = hist + (blockIdx.x == 0 ? 0 : NN_BINS);
+  const int per = blockIdx.x == 0 ? NN_FCLS : 2;
+  int32_t* h = hist + (blockIdx.x == 0 ? 0 : NN_NODE_BINS) + per * threadIdx.x;
   const int t = threadIdx.x;
-  const int v0 = h[per * t], v1 = per == 2 ? h[2 * t + 1] : 0;
-  s[t] = v0 + v1;
+  int32_t v[NN_FCLS];
+  int sum = 0;
+#pragma unroll
+  for (int k = 0; k < NN_FCLS; k++) { v[k] = k < per ? h[k] : 0; sum += v[k]; }
+  s[t] = sum;
   __syncthreads();
   for (int o = 1; o < NN_BINS; o <<= 1) {
     const int x = t >= o ? s[t - o] : 0;
@@ -132,15 +157,16 @@ __global__ void __launch_bounds__(NN_BINS) nn_scan_kernel(int32_t* __restrict__ 
     s[t] += x;
     __syncthreads();
   }
-  const int excl = s[t] - (v0 + v1);
-  h[per * t] = excl;
-  if (per == 2) h[2 * t + 1] = excl + v0;
+  int excl = s[t] - sum;
+#pragma unroll
+  for (int k = 0; k < NN_FCLS; k++)
+    if (k < per) { h[k] = excl; excl += v[k]; }
 }
 
 __global__ void __launch_bounds__(256) nn_scatter_kernel(const NNSortArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int key = -1;
-  if (i < a.n_nodes + a.K) key = (i < a.n_nodes ? 0 : NN_BINS) + a.bin[i];
+  if (i < a.n_nodes + a.K) key = (i < a.n_nodes ? 0 : NN_NODE_BINS) + a.bin[i];
   const unsigned peers = __match_any_sync(FULL_MASK, key);
   const int leader = __ffs(peers) - 1;
   int base = 0;
@@ -175,6 +201,15 @@ __global__ void __launch_bounds__(256) nn_scatter_kernel(const NNSortArgs a) {
 // optimise key of a sample is its straight distance from the root to within millimetres, and the box bound (distance to
 // the tile's box + the tile's smallest costE) is loose by the size of the box in every tile near that line; the projected
 // bound keeps the correlation between cost and position inside the tile (2.3e5 nodes: 321 -> 47 tiles per sample).
+// And the FEASIBILITY bound.  feasibleNode (rrtplanner.cpp:271-289) accepts a node for a sample S only when w = S - rb (rb:
+// the end of the node's own reference) lies within 45 degrees of the reference's direction dp.  Every dp of direction class
+// c lies within 11.25 degrees of the class centre f_c, so a feasible w lies within 56.25 degrees of f_c and  S . f_c > rb . f_c.
+// With  feas[t][c] = min over the tile's nodes of class c of rb . f_c  (+inf for a class the tile does not hold), no node of
+// the tile can be feasible for S when  S . f_c < feas[t][c]  for every class, and the tile is skipped.  On a dense tree most
+// nodes around a sample are infeasible for it — a node stops some 5 m short of the end of its reference, so the references
+// of the nodes near S end beyond S — and the feasible ones sit on the far rim of the disc the distance bound leaves; the
+// order by class inside a bin keeps the few nodes whose references point sideways or backwards (which can be feasible from
+// anywhere) out of most tiles.  A node with a zero-length or non-finite reference direction makes its tile unskippable.
 #define NN_DIRS 9  // -40 .. 40 degrees from the axis
 __device__ __forceinline__ void nn_dir(int k, float* c, float* s) {
   const float a = (float)(k - NN_DIRS / 2) * 0.17453293f;
@@ -182,13 +217,20 @@ __device__ __forceinline__ void nn_dir(int k, float* c, float* s) {
 }
 __global__ void __launch_bounds__(NEAREST_TILE) nn_tile_kernel(const int32_t* __restrict__ sbin, const float* __restrict__ ce,
                                                                 const float* __restrict__ fx, const float* __restrict__ fy,
+                                                                const float* __restrict__ frx, const float* __restrict__ fry,
+                                                                const float* __restrict__ fdx, const float* __restrict__ fdy,
                                                                 float cb, float sb,
                                                                 int n_nodes, float u0, float bin_w, float v0, float vbin_w,
                                                                 int nl_log2, float* __restrict__ ulo, float* __restrict__ uhi,
                                                                 float* __restrict__ vlo, float* __restrict__ vhi,
-                                                                float* __restrict__ cemin, float* __restrict__ proj) {
+                                                                float* __restrict__ cemin, float* __restrict__ proj,
+                                                                float* __restrict__ feas) {
   __shared__ float smn[NEAREST_TILE / 32];
   __shared__ float spr[NEAREST_TILE / 32][NN_DIRS];
+  __shared__ float sfe[NEAREST_TILE / 32][NN_FCLS];
+  __shared__ int s_bad;
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
   const int t = blockIdx.x, i = t * NEAREST_TILE + threadIdx.x;
   float mn = INFINITY;
   float c = 0.0f, u = 0.0f, v = 0.0f;
@@ -207,7 +249,31 @@ __global__ void __launch_bounds__(NEAREST_TILE) nn_tile_kernel(const int32_t* __
     for (int o = 16; o > 0; o >>= 1) g = fminf(g, __shfl_xor_sync(FULL_MASK, g, o));
     if ((threadIdx.x & 31) == 0) spr[threadIdx.x >> 5][k] = g;
   }
+  {
+    int cls = -1;
+    float ru = 0.0f, rv = 0.0f;
+    if (i < n_nodes) {
+      const float rx = frx[i], ry = fry[i], dx = fdx[i], dy = fdy[i];
+      ru = rx * cb + ry * sb; rv = ry * cb - rx * sb;
+      cls = sbin[i] & (NN_FCLS - 1);   // (the class the sort used: nn_bin_kernel)
+      if (!(fabsf(ru) < 1.0e15f) || !(fabsf(rv) < 1.0e15f) || !(fabsf(dx) < 1.0e15f) || !(fabsf(dy) < 1.0e15f) ||
+          (dx == 0.0f && dy == 0.0f)) s_bad = 1;
+    }
+    for (int k = 0; k < NN_FCLS; k++) {
+      float m = cls == k ? ru * c_nn_fdir[k].x + rv * c_nn_fdir[k].y : INFINITY;
+      if (!(m == m)) m = -INFINITY;
+      for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(FULL_MASK, m, o));
+      if ((threadIdx.x & 31) == 0) sfe[threadIdx.x >> 5][k] = m;
+    }
+  }
   __syncthreads();
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + NN_FCLS) {
+    const int k = threadIdx.x - 32;
+    float m = sfe[0][k];
+    for (int w = 1; w < NEAREST_TILE / 32; w++) m = fminf(m, sfe[w][k]);
+    // (less the float rounding of rb . f_c; an empty class stays at +inf)
+    feas[(size_t)t * NN_FCLS + k] = s_bad ? -INFINITY : m == INFINITY ? INFINITY : m - (1.0e-3f + 1.0e-5f * fabsf(m));
+  }
   if (threadIdx.x < NN_DIRS) {
     float g = spr[0][threadIdx.x];
     for (int w = 1; w < NEAREST_TILE / 32; w++) g = fminf(g, spr[w][threadIdx.x]);
@@ -218,7 +284,8 @@ __global__ void __launch_bounds__(NEAREST_TILE) nn_tile_kernel(const int32_t* __
     for (int w = 1; w < NEAREST_TILE / 32; w++) mn = fminf(mn, smn[w]);
     const int b0 = sbin[t * NEAREST_TILE], b1 = sbin[min(t * NEAREST_TILE + NEAREST_TILE - 1, n_nodes - 1)];
     const int ns = NN_BINS >> nl_log2, nl = 1 << nl_log2;
-    const int s0 = b0 >> nl_log2, s1 = b1 >> nl_log2, l0 = b0 & (nl - 1), l1 = b1 & (nl - 1);
+    const int p0 = b0 / NN_FCLS, p1 = b1 / NN_FCLS;   // spatial bins of the first and the last node
+    const int s0 = p0 >> nl_log2, s1 = p1 >> nl_log2, l0 = p0 & (nl - 1), l1 = p1 & (nl - 1);
     ulo[t] = s0 <= 0 ? -INFINITY : u0 + (float)s0 * bin_w - 0.01f;
     uhi[t] = s1 >= ns - 1 ? INFINITY : u0 + (float)(s1 + 1) * bin_w + 0.01f;
     // within one slab the nodes are ordered by lateral bin; a tile that spans several slabs covers every lateral position
@@ -333,6 +400,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
   __shared__ uint16_t s_idx[NEAREST_WARPS][NEAREST_TILE];
   __shared__ uint16_t s_idx2[NEAREST_WARPS][NEAREST_TILE];
   __shared__ int s_start;
+  __shared__ float s_sp[NEAREST_WARPS][NN_FCLS];   // sample . f_c (+ rounding) for the feasibility bound of a tile
   __shared__ unsigned s_mask[3][2];   // per chunk of 32 tiles: wanted by any sample / axis-open for any sample (3 in rotation)
   const NearestSorted& so = a.so;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -357,6 +425,8 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
   float proj_s = 0.0f;
   if (lane < NN_DIRS) { float c, sn; nn_dir(lane, &c, &sn); proj_s = 0.999f * (su * c + sv * sn); }
   const float proj_tol = 2.0e-3f + 1.0e-5f * (fabsf(su) + fabsf(sv));
+  if (lane < NN_FCLS) s_sp[warp][lane] = su * c_nn_fdir[lane].x + sv * c_nn_fdir[lane].y + proj_tol;
+  __syncwarp();
   float lk = INFINITY;  // entry `lane` of the list (lanes >= 10 stay at +inf / INT_MAX and never take part)
   int lid = INT_MAX;
   float T = INFINITY;   // key and id of the 10th entry (warp-uniform)
@@ -379,7 +449,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
       const float us = su - (fabsf(lead) < 1.0e6f ? lead : 0.0f);
       const int b = (nn_bin_of(us, so.u0, so.inv_bin, NN_BINS >> so.nl_log2) << so.nl_log2) |
                     nn_bin_of(sv, so.v0, so.inv_vbin, 1 << so.nl_log2);
-      const int first = b > 0 ? so.bin_end[b - 1] : 0;
+      const int first = b > 0 ? so.bin_end[b * NN_FCLS - 1] : 0;
       start = min(max(first, 0) / NEAREST_TILE, so.n_tiles - 1);
     }
     s_start = start;
@@ -422,6 +492,18 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
 #pragma unroll
         for (int k = 0; k < NN_DIRS; k++) bnd = fmaxf(bnd, pr[k] + proj_all[k]);
         lb = fmaxf(lb, bnd - proj_tol);   // (fmaxf drops a NaN operand: the other bound stands)
+      }
+      // feasibility bound (nn_tile_kernel): a class whose reference ends are not all beyond the sample?
+      {
+        const float4* fe = reinterpret_cast<const float4*>(so.tile_feas + (size_t)tl * NN_FCLS);
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < NN_FCLS / 4; k++) {
+          const float4 f = fe[k];
+          any |= !(s_sp[warp][4 * k] < f.x) | !(s_sp[warp][4 * k + 1] < f.y) | !(s_sp[warp][4 * k + 2] < f.z) |
+                 !(s_sp[warp][4 * k + 3] < f.w);
+        }
+        if (!any) lb = INFINITY;
       }
       // how far the tile lies BEYOND the sample in the direction of travel: monotone along that direction whatever the
       // sample's own position is.  (The lateral interval and the costs are not monotone along the order — the root, 30 m
