@@ -861,7 +861,7 @@ static int nearest_dev(clrrt_ctx* ctx, const double* d_samples, const uint8_t* d
   nn_scan_kernel<<<2, NN_BINS, 0, st>>>(s.hist);
   nn_scatter_kernel<<<(n_el + 255) / 256, 256, 0, st>>>(s);
   nn_tile_kernel<<<n_tiles, NEAREST_TILE, 0, st>>>(s.sbin, s.ce, s.fx, s.fy, s.frx, s.fry, s.fdx, s.fdy, s.cb, s.sb, ctx->n_tree, s.u0, bin_w, s.v0, vbin_w, s.nl_log2, ctx->d_tile_ulo,
-                                                   ctx->d_tile_uhi, ctx->d_tile_vlo, ctx->d_tile_vhi, ctx->d_tile_ce, ctx->d_tile_proj, ctx->d_tile_feas);
+                                                   ctx->d_tile_uhi, ctx->d_tile_vlo, ctx->d_tile_vhi, ctx->d_tile_ce, ctx->d_tile_proj, ctx->d_tile_feas, s.hist + NN_HIST_INTS + 1);
   CK(cudaGetLastError());
   // 2. the search
   NearestArgs a;
@@ -873,7 +873,7 @@ static int nearest_dev(clrrt_ctx* ctx, const double* d_samples, const uint8_t* d
   a.so.fx = s.fx; a.so.fy = s.fy; a.so.frx = s.frx; a.so.fry = s.fry; a.so.fdx = s.fdx; a.so.fdy = s.fdy;
   a.so.tile_ulo = ctx->d_tile_ulo; a.so.tile_uhi = ctx->d_tile_uhi; a.so.tile_vlo = ctx->d_tile_vlo; a.so.tile_vhi = ctx->d_tile_vhi; a.so.tile_ce = ctx->d_tile_ce; a.so.tile_proj = ctx->d_tile_proj; a.so.tile_feas = ctx->d_tile_feas;
   a.so.sample_id = s.sample_id; a.so.cb = s.cb; a.so.sb = s.sb;
-  a.so.bin_end = s.hist; a.so.lead_sum = s.lead_sum; a.so.u0 = s.u0; a.so.inv_bin = s.inv_bin; a.so.v0 = s.v0; a.so.inv_vbin = s.inv_vbin;
+  a.so.bin_end = s.hist; a.so.lead_sum = s.lead_sum; a.so.ce_floor = s.hist + NN_HIST_INTS + 1; a.so.u0 = s.u0; a.so.inv_bin = s.inv_bin; a.so.v0 = s.v0; a.so.inv_vbin = s.inv_vbin;
   a.so.nl_log2 = s.nl_log2;
   const int blocks = (K + NEAREST_WARPS - 1) / NEAREST_WARPS;
   nearest_sorted_kernel<<<blocks, NEAREST_THREADS, 0, ctx->stream>>>(a);

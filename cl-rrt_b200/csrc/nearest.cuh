@@ -65,6 +65,7 @@ struct NearestSorted {
   // offset from a node to the end of its own reference
   const int32_t* bin_end;   // [NN_NODE_BINS] sorted position after the last node of every node bin
   const float* lead_sum;    // sum over the nodes of (reference end - position) . axis
+  const int32_t* ce_floor;  // min(0, smallest costE of the tree) as an order-preserving int (nn_tile_kernel)
   float u0, inv_bin, v0, inv_vbin;
   int32_t nl_log2;
 };
@@ -102,6 +103,10 @@ struct NNSortArgs {
   int32_t* sample_id;
   float* lead_sum;     // hist + NN_HIST_INTS (zeroed with it)
 };
+
+// float <-> int with the same order (for atomicMin on a float)
+__device__ __forceinline__ int nn_ordered(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float nn_unordered(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
 __device__ __forceinline__ int nn_bin_of(float u, float u0, float inv_bin, int nbins) {
   const float b = (u - u0) * inv_bin;
@@ -224,7 +229,7 @@ __global__ void __launch_bounds__(NEAREST_TILE) nn_tile_kernel(const int32_t* __
                                                                 int nl_log2, float* __restrict__ ulo, float* __restrict__ uhi,
                                                                 float* __restrict__ vlo, float* __restrict__ vhi,
                                                                 float* __restrict__ cemin, float* __restrict__ proj,
-                                                                float* __restrict__ feas) {
+                                                                float* __restrict__ feas, int32_t* __restrict__ ce_floor) {
   __shared__ float smn[NEAREST_TILE / 32];
   __shared__ float spr[NEAREST_TILE / 32][NN_DIRS];
   __shared__ float sfe[NEAREST_TILE / 32][NN_FCLS];
@@ -293,6 +298,9 @@ __global__ void __launch_bounds__(NEAREST_TILE) nn_tile_kernel(const int32_t* __
     vlo[t] = (!one || l0 <= 0) ? -INFINITY : v0 + (float)l0 * vbin_w - 0.01f;
     vhi[t] = (!one || l1 >= nl - 1) ? INFINITY : v0 + (float)(l1 + 1) * vbin_w + 0.01f;
     cemin[t] = mn;
+    // min(0, smallest costE of the tree), order-preserving int (zeroed = 0.0f before the launch): what ends a direction of
+    // the optimise-key search must hold for costs below zero too (an uploaded tree may carry any cost)
+    if (mn < 0.0f) atomicMin(ce_floor, nn_ordered(mn));
   }
 }
 
@@ -425,6 +433,9 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
   float proj_s = 0.0f;
   if (lane < NN_DIRS) { float c, sn; nn_dir(lane, &c, &sn); proj_s = 0.999f * (su * c + sv * sn); }
   const float proj_tol = 2.0e-3f + 1.0e-5f * (fabsf(su) + fabsf(sv));
+  // the least any key can be at axis distance da: 0.999 da for the explore key, 0.999 da + the smallest cost of the tree
+  // (0 on any tree the planner grows: the root) for the optimise key
+  const float ce_floor = optimize ? nn_unordered(*so.ce_floor) : 0.0f;
   if (lane < NN_FCLS) s_sp[warp][lane] = su * c_nn_fdir[lane].x + sv * c_nn_fdir[lane].y + proj_tol;
   __syncwarp();
   float lk = INFINITY;  // entry `lane` of the list (lanes >= 10 stay at +inf / INT_MAX and never take part)
@@ -491,7 +502,10 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
         float bnd = -INFINITY;
 #pragma unroll
         for (int k = 0; k < NN_DIRS; k++) bnd = fmaxf(bnd, pr[k] + proj_all[k]);
-        lb = fmaxf(lb, bnd - proj_tol);   // (fmaxf drops a NaN operand: the other bound stands)
+#ifndef NN_NO_PROJ
+        lb = fmaxf(lb, bnd - proj_tol);
+#endif
+          // (fmaxf drops a NaN operand: the other bound stands)
       }
       // feasibility bound (nn_tile_kernel): a class whose reference ends are not all beyond the sample?
       {
@@ -503,13 +517,15 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
           any |= !(s_sp[warp][4 * k] < f.x) | !(s_sp[warp][4 * k + 1] < f.y) | !(s_sp[warp][4 * k + 2] < f.z) |
                  !(s_sp[warp][4 * k + 3] < f.w);
         }
+#ifndef NN_NO_FEAS
         if (!any) lb = INFINITY;
+#endif
       }
       // how far the tile lies BEYOND the sample in the direction of travel: monotone along that direction whatever the
       // sample's own position is.  (The lateral interval and the costs are not monotone along the order — the root, 30 m
       // behind a sample, is the best parent by the optimise key — so they only skip tiles, they never end a direction.)
       const float da = fmaxf(up ? ulo - su : su - uhi, 0.0f);
-      axis_open = !(0.999f * da > T);
+      axis_open = !(0.999f * da + ce_floor > T);
     }
     const unsigned wm = __ballot_sync(FULL_MASK, live && tl >= 0 && tl < so.n_tiles && !(lb > T));
     const unsigned om = __ballot_sync(FULL_MASK, axis_open);

@@ -156,3 +156,54 @@ def test_equal_keys_follow_std_sort_for_single_sample_searches(clrrt, planner, g
         planner.set_tie_mode(1)
     assert planner.tie_sorts() > 0
     print(f"equal keys: {differ} of {len(smp)} lists differ between the two tie rules; {planner.tie_sorts()} searches repeated std::sort on the host")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [0, 1])
+def test_sorted_search_bounds_on_an_adversarial_tree(clrrt, seed):
+    """The tile bounds of the sorted search (box, projected cost, feasibility by direction class) only ever skip what the
+    exact tests reject — on a tree that breaks every regularity a grown tree has: references in all directions (also of zero
+    length, also ending far from their node), costs unrelated to the distance from the root (zero, huge, negative), nodes
+    outside the binned range, duplicated nodes.  Storage-order search (every node of every tile) = sorted search, for both
+    keys and 1, 4, 16 lateral bins."""
+    import bench
+    rng = np.random.default_rng(seed)
+    n, K = 120000, 2048
+    nodes = np.zeros(n, clrrt.NODE_DTYPE)
+    nodes[0] = clrrt.root_node(bench.C1_CAR)[0]
+    x = rng.uniform(-20.0, 80.0, n); y = rng.uniform(-12.0, 12.0, n)
+    x[:50] = rng.uniform(-300.0, 300.0, 50)            # outside the bins
+    th = rng.uniform(-np.pi, np.pi, n)
+    st = nodes["state"]; st[1:, 0] = x[1:]; st[1:, 1] = y[1:]; st[1:, 2] = th[1:]; st[1:, 4] = 5.0
+    ang = rng.uniform(-np.pi, np.pi, n)                # direction of the node's own reference: anything
+    ang[rng.random(n) < 0.7] *= 0.2                    # most roughly forward, like a grown tree
+    lead = rng.uniform(0.0, 8.0, n); length = rng.uniform(0.0, 6.0, n)
+    length[rng.random(n) < 0.01] = 0.0                 # zero-length references
+    rb = np.stack([x + lead * np.cos(th), y + lead * np.sin(th)], 1)
+    rf = rb - length[:, None] * np.stack([np.cos(ang), np.sin(ang)], 1)
+    nodes["ref_back"][1:] = rb[1:]; nodes["ref_front"][1:] = rf[1:]; nodes["ref_vback"][1:] = 5.0
+    ce = np.hypot(x, y) + rng.exponential(0.5, n)
+    ce[rng.random(n) < 0.05] = 0.0
+    ce[rng.random(n) < 0.02] = 1.0e6
+    ce[rng.random(n) < 0.02] *= -1.0
+    nodes["costE"][1:] = ce[1:].astype(np.float32)
+    nodes["parent"][1:] = 0
+    nodes["n_ref"][1:] = 2
+    nodes[n // 2:n // 2 + 500] = nodes[1000:1500]      # duplicates: equal keys, the lower node id wins
+    nodes["parent"][n // 2:n // 2 + 500] = 0
+    pl = clrrt.Planner(device=0, tree_capacity=n + 16, max_round=K)
+    try:
+        pl.set_query(bench.C1_CAR, bench.C1_GOAL, bench.VMAX)
+        pl.tree_reset(nodes)
+        s = np.stack([rng.uniform(-5.0, 70.0, K), rng.uniform(-9.0, 9.0, K)], 1)
+        for h in (np.zeros(K, np.uint8), np.ones(K, np.uint8), (rng.random(K) < 0.3).astype(np.uint8)):
+            pl.set_nearest_mode(2)
+            want = pl.nearest_batch(s, h)
+            assert (want[2] > 0).mean() > 0.5
+            for mode in (16, 18, 20, 0):
+                pl.set_nearest_mode(mode)
+                got = pl.nearest_batch(s, h)
+                for a, b in zip(got, want):
+                    assert np.array_equal(a, b), f"mode {mode}"
+    finally:
+        pl.close()
