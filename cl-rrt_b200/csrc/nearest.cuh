@@ -147,13 +147,22 @@ __global__ void __launch_bounds__(256) nn_bin_kernel(const NNSortArgs a) {
 // 2 * NN_BINS sample bins, two per thread)
 __global__ void __launch_bounds__(NN_BINS) nn_scan_kernel(int32_t* __restrict__ hist) {
   __shared__ int32_t s[NN_BINS];
-  const int per = blockIdx.x == 0 ? NN_FCLS : 2;
-  int32_t* h = hist + (blockIdx.x == 0 ? 0 : NN_NODE_BINS) + per * threadIdx.x;
+  int32_t* h = hist + (blockIdx.x == 0 ? NN_FCLS * threadIdx.x : NN_NODE_BINS + 2 * threadIdx.x);
   const int t = threadIdx.x;
   int32_t v[NN_FCLS];
   int sum = 0;
+  if (blockIdx.x == 0) {   // 64 bytes per thread: four 16-byte loads
 #pragma unroll
-  for (int k = 0; k < NN_FCLS; k++) { v[k] = k < per ? h[k] : 0; sum += v[k]; }
+    for (int k = 0; k < NN_FCLS / 4; k++) {
+      const int4 q = reinterpret_cast<const int4*>(h)[k];
+      v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < NN_FCLS; k++) v[k] = k < 2 ? h[k] : 0;
+  }
+#pragma unroll
+  for (int k = 0; k < NN_FCLS; k++) sum += v[k];
   s[t] = sum;
   __syncthreads();
   for (int o = 1; o < NN_BINS; o <<= 1) {
@@ -164,8 +173,13 @@ __global__ void __launch_bounds__(NN_BINS) nn_scan_kernel(int32_t* __restrict__ 
   }
   int excl = s[t] - sum;
 #pragma unroll
-  for (int k = 0; k < NN_FCLS; k++)
-    if (k < per) { h[k] = excl; excl += v[k]; }
+  for (int k = 0; k < NN_FCLS; k++) { const int c = v[k]; v[k] = excl; excl += c; }
+  if (blockIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NN_FCLS / 4; k++) reinterpret_cast<int4*>(h)[k] = make_int4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  } else {
+    h[0] = v[0]; h[1] = v[1];
+  }
 }
 
 __global__ void __launch_bounds__(256) nn_scatter_kernel(const NNSortArgs a) {
