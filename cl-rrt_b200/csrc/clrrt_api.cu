@@ -825,7 +825,7 @@ static int nearest_reference_ties(clrrt_ctx* ctx, const double* d_samples, const
 
 static int nearest_dev(clrrt_ctx* ctx, const double* d_samples, const uint8_t* d_heur, int K, int32_t* d_cand,
                        float* d_key, int32_t* d_count, bool window = false) {
-  const bool sorted = ctx->nn_mode == 1 || (ctx->nn_mode == 0 && (double)K * (double)ctx->n_tree >= NN_SORT_MIN_PAIRS);
+  const bool sorted = ctx->n_tree > 0 && (ctx->nn_mode == 1 || (ctx->nn_mode == 0 && (double)K * (double)ctx->n_tree >= NN_SORT_MIN_PAIRS));
   const bool ref_ties = K == 1 && ctx->tie_mode == 1 && !window;  // windows flag ties themselves (tie_window_kernel)
   if (ref_ties && !d_key) d_key = ctx->d_key;
   if (!sorted) {

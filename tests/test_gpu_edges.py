@@ -158,3 +158,34 @@ def test_non_finite_samples_and_full_tree(clrrt, planner):
     assert small.tree_size() == 64
     assert small.tree_download().tobytes() == full[:64].tobytes()
     small.close()
+
+
+def test_search_without_a_tree_and_with_non_finite_samples(clrrt):
+    """A context that holds no tree yet refuses a search (CLRRT_ERR_STATE, whichever search is selected), and non-finite
+    samples go through the sorted search like through the storage-order one: same lists, no candidates for them."""
+    pl = clrrt.Planner(device=0, tree_capacity=1 << 12, max_round=1 << 10)
+    try:
+        pl.set_query(CAR, GOAL, 5.0)
+        s, h = clrrt.draw_samples(GOAL, 64, seed=3)
+        for mode in (0, 1, 2, 18):
+            pl.set_nearest_mode(mode)
+            with pytest.raises(clrrt.ClrrtError, match="-4"):
+                pl.nearest_batch(s, h)
+        pl.set_obstacles(scene_c1_boxes())
+        pl.tree_reset(clrrt.root_node(CAR))
+        pl.set_nearest_mode(0)
+        for seed in (6, 7, 8):
+            s2, h2 = clrrt.draw_samples(GOAL, 1024, seed=seed)
+            pl.expand_round(s2, h2)
+        s, h = clrrt.draw_samples(GOAL, 512, seed=9)
+        s[3] = [np.nan, 1.0]; s[4] = [1.0, np.nan]; s[7] = [np.inf, 0.0]; s[8] = [-np.inf, np.inf]; s[11] = [1e30, -1e30]
+        pl.set_nearest_mode(2)
+        want = pl.nearest_batch(s, h)
+        for mode in (1, 17, 18, 20):
+            pl.set_nearest_mode(mode)
+            got = pl.nearest_batch(s, h)
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b), f"mode {mode}"
+        assert (want[2][[3, 4]] == 0).all()   # NaN coordinates: nothing is feasible
+    finally:
+        pl.close()
