@@ -44,7 +44,7 @@ class SeqStats(C.Structure):
     _fields_ = [("iterations", C.c_int64), ("sim_steps", C.c_int64), ("rollouts", C.c_int64), ("windows", C.c_int32),
                 ("speculated", C.c_int32), ("nodes_added", C.c_int32), ("tree_size", C.c_int32),
                 ("exact_fallbacks", C.c_int32), ("ms_total", C.c_float), ("ms_search", C.c_float), ("ms_prepare", C.c_float),
-                ("ms_rollout", C.c_float), ("ms_commit", C.c_float), ("reserved", C.c_int32)]
+                ("ms_rollout", C.c_float), ("ms_commit", C.c_float), ("tie_checks_same", C.c_int32)]
 
 
 class Counters(C.Structure):

@@ -823,6 +823,57 @@ static int nearest_reference_ties(clrrt_ctx* ctx, const double* d_samples, const
   return CLRRT_OK;
 }
 
+// Sequential windows: sample 0 of a window has a candidate whose key equals the winner's (or the last place's).  The
+// device orders equal keys by node id, the reference by whatever its std::sort leaves.  This repeats the reference's sort
+// for that one sample (all keys and feasibility flags from tie_check_kernel, the very std::sort call of
+// nearest_reference_ties) and reports whether the OUTCOME is the same: the same candidates in the same order up to and
+// including the winner — or, when no candidate succeeded, the same set of candidates.  Then the window's rollouts stand
+// and only the commit is repeated; otherwise the K = 1 path runs the sample with the reference's list.
+static int window_tie_same_outcome(clrrt_ctx* ctx, const double* d_s, const uint8_t* d_h, bool* same) {
+  cudaStream_t st = ctx->stream;
+  const int n = ctx->n_tree;
+  *same = false;
+  int32_t cand[CLRRT_SORT_LIMIT], cnt = 0;
+  uint32_t word = 0;
+  TieArgs t;
+  t.tree = ctx->tree; t.n_nodes = n; t.sample_xy = d_s; t.heuristic = d_h; t.feas_len = ctx->dprm.feas_len;
+  t.cand = ctx->d_cand; t.key = ctx->d_key; t.count = ctx->d_count; t.all_key = ctx->d_all_key; t.all_feas = ctx->d_all_feas; t.flag = ctx->d_ints + 6;
+  tie_check_kernel<<<(n + 127) / 128, 128, 0, st>>>(t);
+  CK(cudaGetLastError());
+  std::vector<float> key((size_t)n);
+  std::vector<uint8_t> feas((size_t)n);
+  CK(cudaMemcpyAsync(key.data(), ctx->d_all_key, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(feas.data(), ctx->d_all_feas, (size_t)n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(cand, ctx->d_cand, sizeof cand, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&cnt, ctx->d_count, sizeof cnt, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&word, ctx->d_done, sizeof word, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  ctx->tie_sorts++;
+  std::vector<std::pair<int, float>> dVector;
+  for (int nodeid = 0; nodeid != n; nodeid++) dVector.push_back(std::make_pair(nodeid, key[(size_t)nodeid]));
+  std::sort(dVector.begin(), dVector.end(), [](const std::pair<int, float>& a, const std::pair<int, float>& b) { return a.second < b.second; });
+  int32_t ref[CLRRT_SORT_LIMIT], rcnt = 0;
+  for (const auto& e : dVector) {
+    if (feas[(size_t)e.first]) ref[rcnt++] = e.first;
+    if (rcnt == CLRRT_SORT_LIMIT) break;
+  }
+  if (rcnt != cnt) return CLRRT_OK;
+  int sb = -1;
+  for (int r = 0; r < cnt; r++)
+    if ((word >> (16 + r)) & 1u) { sb = r; break; }
+  if (sb >= 0) {
+    for (int r = 0; r <= sb; r++)
+      if (ref[r] != cand[r]) return CLRRT_OK;
+  } else {
+    std::sort(ref, ref + rcnt);
+    std::sort(cand, cand + cnt);
+    for (int r = 0; r < cnt; r++)
+      if (ref[r] != cand[r]) return CLRRT_OK;
+  }
+  *same = true;
+  return CLRRT_OK;
+}
+
 static int nearest_dev(clrrt_ctx* ctx, const double* d_samples, const uint8_t* d_heur, int K, int32_t* d_cand,
                        float* d_key, int32_t* d_count, bool window = false) {
   const bool sorted = ctx->n_tree > 0 && (ctx->nn_mode == 1 || (ctx->nn_mode == 0 && (double)K * (double)ctx->n_tree >= NN_SORT_MIN_PAIRS));
@@ -1250,6 +1301,7 @@ int clrrt_expand_sequential(clrrt_ctx* ctx, const double* sample_xy, const uint8
       }
       SeqCommitArgs c;
       c.tree = ctx->tree; c.stage = ctx->stage; c.n_tree = ctx->n_tree; c.capacity = ctx->cap; c.w = w; c.n_ranks = CLRRT_SORT_LIMIT;
+      c.skip_tie_first = 0;
       c.sample_xy = d_s; c.heuristic = d_h; c.key = ctx->d_key; c.count = ctx->d_count; c.sample_word = ctx->d_done;
       c.valid = ctx->d_valid; c.slot = ctx->d_slot; c.res_code = ctx->d_res_code; c.res_steps = ctx->d_res_steps; c.tie_flag = d_tie;
       c.feas_len = ctx->dprm.feas_len; c.counters = ctx->d_counters; c.out = ctx->d_ints + 8;
@@ -1263,6 +1315,21 @@ int clrrt_expand_sequential(clrrt_ctx* ctx, const double* sample_xy, const uint8
         cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]); cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[5]);
         cudaEventElapsedTime(&c2, ctx->ev[5], ctx->ev[2]); cudaEventElapsedTime(&d, ctx->ev[2], ctx->ev[4]);
         acc.ms_search += a; acc.ms_prepare += b; acc.ms_rollout += c2; acc.ms_commit += d;
+      }
+      if (ctx->h_ints[10] == 1 && ctx->h_ints[8] == 0) {
+        // sample 0's outcome may hang on the order of equal keys: if the reference's own sort gives the same outcome, the
+        // window's rollouts stand and the commit is repeated with that check waived for sample 0
+        bool same = false;
+        if ((rc = window_tie_same_outcome(ctx, d_s, d_h, &same))) return rc;
+        if (same) {
+          CK(cudaMemsetAsync(ctx->d_ints + 8, 0, 3 * sizeof(int32_t), st));
+          c.skip_tie_first = 1;
+          seq_commit_kernel<<<1, SEQ_THREADS, 0, st>>>(c);
+          CK(cudaGetLastError());
+          CK(cudaMemcpyAsync(ctx->h_ints + 8, ctx->d_ints + 8, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+          CK(cudaStreamSynchronize(st));
+          acc.tie_checks_same++;
+        }
       }
       const int committed = ctx->h_ints[8], appended = ctx->h_ints[9], stop = ctx->h_ints[10];
       ctx->n_tree += appended;

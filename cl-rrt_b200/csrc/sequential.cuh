@@ -12,9 +12,10 @@
 //   (feasibleNode, rrtplanner.cpp:271-289) with a key (dubinsDistance [+ costE], :227-268) at or below the winner's key —
 //   or, when no candidate succeeded, at or below the key of the 10th candidate (any feasible new node when the list
 //   holds fewer than 10).  Candidates after the winner are never tried (:150-160), so new nodes that sort after it do
-//   not matter.  The first sample for which that fails (or whose own list contains two equal keys, whose order is
-//   libstdc++'s std::sort's, see tie_check_kernel) ends the window: it and the samples after it are run again in the next
-//   window, against the tree that now contains the committed nodes.  Sample 0 of a window is never speculative.
+//   not matter.  The first sample for which that fails (or whose outcome hangs on the order of two equal keys, which is
+//   libstdc++'s std::sort's: tie_window_kernel, seq_commit_kernel) ends the window: it and the samples after it are run
+//   again in the next window, against the tree that now contains the committed nodes.  Sample 0 of a window is never
+//   speculative.
 //
 // seq_commit_kernel does this on the device (one block): for each sample in order, every new node is tested in
 // parallel (one thread per new node), then the sample's node and its goal-biased child are appended to the tree SoA
@@ -28,8 +29,13 @@
 #define SEQ_MAX_WINDOW 64
 #define SEQ_THREADS 128   // >= 2 * SEQ_MAX_WINDOW: one thread per node the window may have appended
 
-// flag[j] |= 1 when the candidate list of window sample j depends on how equal keys are ordered: a feasible node shares
-// its key with a list entry (cf. tie_check_kernel, K = 1).  grid = (ceil(n_nodes / 128), w).
+// flag[j]: which entries of window sample j's candidate list share their key with another feasible node (cf.
+// tie_check_kernel, K = 1) — bit r: some feasible node other than entry r has entry r's key; bit 10: a feasible node
+// OUTSIDE the list has the key of the last entry (it could have taken that place); bit 11: a NaN key.  The reference's
+// order of equal keys is libstdc++'s std::sort's; whether that order can change the OUTCOME is decided in
+// seq_commit_kernel, where the winner is known.  grid = (ceil(n_nodes / 128), w).
+#define SEQ_TIE_OUTSIDE (1 << CLRRT_SORT_LIMIT)
+#define SEQ_TIE_NAN (2 << CLRRT_SORT_LIMIT)
 struct TieWindowArgs {
   NodeSoA tree;
   int32_t n_nodes;
@@ -51,17 +57,22 @@ __global__ void __launch_bounds__(128) tie_window_kernel(const TieWindowArgs a) 
   if (a.heuristic[j]) key = a.tree.costE[i] + key;  // rrtplanner.cpp:254
   const float* kj = a.key + (size_t)j * CLRRT_SORT_LIMIT;
   const int32_t* cj = a.cand + (size_t)j * CLRRT_SORT_LIMIT;
-  bool tie = !(key == key);
-  for (int r = 0; r < cnt; r++)
-    if (key == kj[r] && cj[r] != i) tie = true;
-  if (!tie) return;
+  int bits = !(key == key) ? SEQ_TIE_NAN : 0;
+  bool listed = false;
+  for (int r = 0; r < cnt; r++) {
+    if (cj[r] == i) listed = true;
+    else if (key == kj[r]) bits |= 1 << r;
+  }
+  if (!listed && (bits & (1 << (CLRRT_SORT_LIMIT - 1)))) bits |= SEQ_TIE_OUTSIDE;
+  if (!bits) return;
   const double rbx = a.tree.rbx[i], rby = a.tree.rby[i];
-  if (feasible_node(sx, sy, rbx, rby, rbx - a.tree.rfx[i], rby - a.tree.rfy[i], a.tree.angPar[i], a.feas_len)) atomicOr(&a.flag[j], 1);
+  if (feasible_node(sx, sy, rbx, rby, rbx - a.tree.rfx[i], rby - a.tree.rfy[i], a.tree.angPar[i], a.feas_len)) atomicOr(&a.flag[j], bits);
 }
 
 struct SeqCommitArgs {
   NodeSoA tree, stage;
   int32_t n_tree, capacity, w, n_ranks;
+  int32_t skip_tie_first;      // 1: the host has checked sample 0's equal keys against the reference's order (same outcome)
   const double* sample_xy;
   const uint8_t* heuristic;
   const float* key;            // [w][10]
@@ -102,10 +113,20 @@ __global__ void __launch_bounds__(SEQ_THREADS) seq_commit_kernel(const SeqCommit
   for (int j = 0; j < a.w; j++) {
     const int n_new = s_new;
     // ---- does the speculation of sample j stand? ---------------------------------------------------------------------
-    if (a.tie_flag[j]) { stop = 1; break; }  // equal keys: the reference's order is std::sort's (host path, K = 1)
     const int cnt = a.count[j];
     const int sb = __ffs(a.sample_word[j] >> 16) - 1;
     const bool won = sb >= 0 && sb < cnt;
+    // Equal keys: the reference's order is std::sort's (host path, K = 1).  The order can only change the outcome when it
+    // involves the WINNER (another feasible node with the winner's key may be tried first and succeed too) or, when no
+    // candidate succeeded, the last place of a full list (a node outside it with the same key may have taken that place
+    // and succeed).  Equal keys among candidates that fail anyway — tried in either order, counted either way — and
+    // among candidates after the winner, which are never tried (rrtplanner.cpp:150-160), leave the tree and the counters
+    // as they are.
+    {
+      const int tb = a.tie_flag[j];
+      const bool matters = (tb & SEQ_TIE_NAN) || (won ? ((tb >> sb) & 1) : (cnt == CLRRT_SORT_LIMIT && (tb & SEQ_TIE_OUTSIDE)));
+      if (matters && !(j == 0 && a.skip_tie_first)) { stop = 1; break; }
+    }
     if (j > 0 && n_new > 0) {
       float T;  // a feasible new node with key <= T would have been tried before the speculative outcome was reached
       if (won) T = a.key[(size_t)j * CLRRT_SORT_LIMIT + sb];

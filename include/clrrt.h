@@ -215,12 +215,12 @@ typedef struct clrrt_seq_stats {
   int32_t windows;          /* speculative windows run */
   int32_t speculated;       /* samples speculated in total (>= iterations; the excess was run twice) */
   int32_t nodes_added, tree_size;
-  int32_t exact_fallbacks;  /* samples whose candidate list depended on std::sort's order of equal keys (host route) */
+  int32_t exact_fallbacks;  /* samples whose OUTCOME depended on std::sort's order of equal keys: run by the K = 1 host route */
   float ms_total;           /* wall clock of the call */
   /* device time summed over the windows: candidate search; launch order + set-up; the rollout kernel; winner selection,
    * equal-key check and in-order commit */
   float ms_search, ms_prepare, ms_rollout, ms_commit;
-  int32_t reserved;
+  int32_t tie_checks_same;  /* samples whose equal keys were checked against the reference's sort and gave the same outcome */
 } clrrt_seq_stats;
 int clrrt_expand_sequential(clrrt_ctx* ctx, const double* sample_xy, const uint8_t* heuristic, int n, int window,
                             clrrt_seq_stats* stats);
