@@ -516,10 +516,9 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
         float bnd = -INFINITY;
 #pragma unroll
         for (int k = 0; k < NN_DIRS; k++) bnd = fmaxf(bnd, pr[k] + proj_all[k]);
-#ifndef NN_NO_PROJ
-        lb = fmaxf(lb, bnd - proj_tol);
+#ifndef NN_NO_PROJ  // (diagnostic builds switch the bound off)
+        lb = fmaxf(lb, bnd - proj_tol);   // (fmaxf drops a NaN operand: the other bound stands)
 #endif
-          // (fmaxf drops a NaN operand: the other bound stands)
       }
       // feasibility bound (nn_tile_kernel): a class whose reference ends are not all beyond the sample?
       {
@@ -531,7 +530,7 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
           any |= !(s_sp[warp][4 * k] < f.x) | !(s_sp[warp][4 * k + 1] < f.y) | !(s_sp[warp][4 * k + 2] < f.z) |
                  !(s_sp[warp][4 * k + 3] < f.w);
         }
-#ifndef NN_NO_FEAS
+#ifndef NN_NO_FEAS  // (diagnostic builds switch the bound off)
         if (!any) lb = INFINITY;
 #endif
       }
@@ -551,106 +550,106 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
     if (threadIdx.x == 0) { s_mask[(chunk + 2) % 3][0] = 0; s_mask[(chunk + 2) % 3][1] = 0; NN_STAT(0, 1); }
     if (!(open_any >> 31)) { if (up) open_up = false; else open_dn = false; }
     while (want_any) {
-    const int bit = __ffs(want_any) - 1;
-    want_any &= want_any - 1;
-    const int t = up ? first + bit : first - bit;
-    const bool want = live && !(__shfl_sync(FULL_MASK, lb, bit) > T) && ((wm >> bit) & 1u);
-    // T has moved since the chunk was voted on: is the tile still needed?  (This barrier also separates the reads of the
-    // previous tile from the loads of this one.)
-    if (!__syncthreads_or(want ? 1 : 0)) continue;
-    const int base = t * NEAREST_TILE;
-    const int n = min(NEAREST_TILE, so.n_nodes - base);
-    if (threadIdx.x == 0) NN_STAT(1, 1);
-    if ((int)threadIdx.x < n) {
-      const int g = base + threadIdx.x;
-      s_fx[threadIdx.x] = so.fx[g]; s_fy[threadIdx.x] = so.fy[g]; s_ce[threadIdx.x] = so.ce[g];
-      s_frx[threadIdx.x] = so.frx[g]; s_fry[threadIdx.x] = so.fry[g];
-      s_fdx[threadIdx.x] = so.fdx[g]; s_fdy[threadIdx.x] = so.fdy[g];
-    }
-    __syncthreads();
-    if (want) {
-      // stage 1: distance bound against T, then the float pre-test of feasibility for the nodes that pass it
-      // The nodes of a tile are stored in axis order.  Explore key: they are taken from the sample's own axis position
-      // outwards (tiles before the sample: last node first; the sample's own tile: the part before the sample backwards, then
-      // the rest forwards).  Optimise key: in storage order, root side first.  The list does not depend on the order — it is
-      // ordered by (key, node id) — but its cost does: best first, T is tight after a few insertions and stage 1 drops almost
-      // everything that follows; worst first, every feasible node of the tile is inserted in turn (C3, 4096 nodes, per sample:
-      // 61 -> 13 insertions with the explore key, 104 -> 10 with the optimise key).
-      int split = 0;
-      if (!optimize) {
-        if (so.tile_uhi[t] < su) split = n;
-        else if (!(so.tile_ulo[t] > su)) {
-          for (int i0 = 0; i0 < n; i0 += 32) {
-            const int i = i0 + lane;
-            split += __popc(__ballot_sync(FULL_MASK, i < n && s_fx[i] * so.cb + s_fy[i] * so.sb < su));
+      const int bit = __ffs(want_any) - 1;
+      want_any &= want_any - 1;
+      const int t = up ? first + bit : first - bit;
+      const bool want = live && !(__shfl_sync(FULL_MASK, lb, bit) > T) && ((wm >> bit) & 1u);
+      // T has moved since the chunk was voted on: is the tile still needed?  (This barrier also separates the reads of the
+      // previous tile from the loads of this one.)
+      if (!__syncthreads_or(want ? 1 : 0)) continue;
+      const int base = t * NEAREST_TILE;
+      const int n = min(NEAREST_TILE, so.n_nodes - base);
+      if (threadIdx.x == 0) NN_STAT(1, 1);
+      if ((int)threadIdx.x < n) {
+        const int g = base + threadIdx.x;
+        s_fx[threadIdx.x] = so.fx[g]; s_fy[threadIdx.x] = so.fy[g]; s_ce[threadIdx.x] = so.ce[g];
+        s_frx[threadIdx.x] = so.frx[g]; s_fry[threadIdx.x] = so.fry[g];
+        s_fdx[threadIdx.x] = so.fdx[g]; s_fdy[threadIdx.x] = so.fdy[g];
+      }
+      __syncthreads();
+      if (want) {
+        // stage 1: distance bound against T, then the float pre-test of feasibility for the nodes that pass it
+        // The nodes of a tile are stored in axis order.  Explore key: they are taken from the sample's own axis position
+        // outwards (tiles before the sample: last node first; the sample's own tile: the part before the sample backwards, then
+        // the rest forwards).  Optimise key: in storage order, root side first.  The list does not depend on the order — it is
+        // ordered by (key, node id) — but its cost does: best first, T is tight after a few insertions and stage 1 drops almost
+        // everything that follows; worst first, every feasible node of the tile is inserted in turn (C3, 4096 nodes, per sample:
+        // 61 -> 13 insertions with the explore key, 104 -> 10 with the optimise key).
+        int split = 0;
+        if (!optimize) {
+          if (so.tile_uhi[t] < su) split = n;
+          else if (!(so.tile_ulo[t] > su)) {
+            for (int i0 = 0; i0 < n; i0 += 32) {
+              const int i = i0 + lane;
+              split += __popc(__ballot_sync(FULL_MASK, i < n && s_fx[i] * so.cb + s_fy[i] * so.sb < su));
+            }
           }
         }
-      }
-      int c1 = 0;
-      for (int i0 = 0; i0 < n; i0 += 32) {
-        const int ii = i0 + lane;
-        const int i = ii < split ? split - 1 - ii : ii;
-        bool keep = false;
-        if (ii < n) keep = stage1_keep(fsx - s_fx[i], fsy - s_fy[i], optimize ? s_ce[i] : 0.0f, T, slack);
-        if (keep) keep = feasible_maybe(fsx, fsy, s_frx[i], s_fry[i], s_fdx[i], s_fdy[i], feas_len2);
-        const unsigned m = __ballot_sync(FULL_MASK, keep);
-        if (keep) s_idx[warp][c1 + __popc(m & lt)] = (uint16_t)i;
-        c1 += __popc(m);
-      }
-      __syncwarp();
-      if (lane == 0) { NN_STAT(2, 1); NN_STAT(3, c1); }
-      // stage 2: feasibility of the survivors, in the reference's double arithmetic
-      int c2 = 0;
-      for (int q0 = 0; q0 < c1; q0 += 32) {
-        const int q = q0 + lane;
-        int i = 0;
-        bool f = false;
-        if (q < c1) {
-          i = s_idx[warp][q];
-          const int g = base + i;
-          f = feasible_node(sx, sy, so.rbx[g], so.rby[g], so.dpx[g], so.dpy[g], so.ang[g], a.feas_len);
+        int c1 = 0;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+          const int ii = i0 + lane;
+          const int i = ii < split ? split - 1 - ii : ii;
+          bool keep = false;
+          if (ii < n) keep = stage1_keep(fsx - s_fx[i], fsy - s_fy[i], optimize ? s_ce[i] : 0.0f, T, slack);
+          if (keep) keep = feasible_maybe(fsx, fsy, s_frx[i], s_fry[i], s_fdx[i], s_fdy[i], feas_len2);
+          const unsigned m = __ballot_sync(FULL_MASK, keep);
+          if (keep) s_idx[warp][c1 + __popc(m & lt)] = (uint16_t)i;
+          c1 += __popc(m);
         }
-        const unsigned m = __ballot_sync(FULL_MASK, f);
-        if (f) s_idx2[warp][c2 + __popc(m & lt)] = (uint16_t)i;
-        c2 += __popc(m);
-      }
-      __syncwarp();
-      if (lane == 0) NN_STAT(4, c2);
-      // stage 3: Dubins keys of the feasible survivors and insertion into the warp's list
-      for (int q0 = 0; q0 < c2; q0 += 32) {
-        const int q = q0 + lane;
-        float key = INFINITY;
-        int idx = INT_MAX;
-        if (q < c2) {
-          const int i = s_idx2[warp][q];
-          const int g = base + i;
-          key = dubins_key(sx, sy, so.nx[g], so.ny[g], so.ca[g], so.sa[g]);
-          if (optimize) key = s_ce[i] + key;  // rrtplanner.cpp:254
-          idx = so.node_id[g];
-        }
-        unsigned wantm = __ballot_sync(FULL_MASK, key < T || (key == T && idx < Tid));
-        while (wantm) {
-          const int src = __ffs(wantm) - 1;
-          wantm &= wantm - 1;
-          const float nk = __shfl_sync(FULL_MASK, key, src);
-          const int nid = __shfl_sync(FULL_MASK, idx, src);
-          if (!(nk < T || (nk == T && nid < Tid))) continue;  // T moved since the ballot
-          if (lane == 0) NN_STAT(5, 1);
-          // position = number of entries ordered before the new one; entries from there on move down one lane
-          const bool before = lk < nk || (lk == nk && lid < nid);
-          const int pos = __popc(__ballot_sync(FULL_MASK, before && lane < CLRRT_SORT_LIMIT));
-          const float uk = __shfl_up_sync(FULL_MASK, lk, 1);
-          const int uid = __shfl_up_sync(FULL_MASK, lid, 1);
-          if (lane < CLRRT_SORT_LIMIT) {
-            if (lane == pos) { lk = nk; lid = nid; }
-            else if (lane > pos) { lk = uk; lid = uid; }
+        __syncwarp();
+        if (lane == 0) { NN_STAT(2, 1); NN_STAT(3, c1); }
+        // stage 2: feasibility of the survivors, in the reference's double arithmetic
+        int c2 = 0;
+        for (int q0 = 0; q0 < c1; q0 += 32) {
+          const int q = q0 + lane;
+          int i = 0;
+          bool f = false;
+          if (q < c1) {
+            i = s_idx[warp][q];
+            const int g = base + i;
+            f = feasible_node(sx, sy, so.rbx[g], so.rby[g], so.dpx[g], so.dpy[g], so.ang[g], a.feas_len);
           }
-          T = __shfl_sync(FULL_MASK, lk, CLRRT_SORT_LIMIT - 1);
-          Tid = __shfl_sync(FULL_MASK, lid, CLRRT_SORT_LIMIT - 1);
+          const unsigned m = __ballot_sync(FULL_MASK, f);
+          if (f) s_idx2[warp][c2 + __popc(m & lt)] = (uint16_t)i;
+          c2 += __popc(m);
         }
+        __syncwarp();
+        if (lane == 0) NN_STAT(4, c2);
+        // stage 3: Dubins keys of the feasible survivors and insertion into the warp's list
+        for (int q0 = 0; q0 < c2; q0 += 32) {
+          const int q = q0 + lane;
+          float key = INFINITY;
+          int idx = INT_MAX;
+          if (q < c2) {
+            const int i = s_idx2[warp][q];
+            const int g = base + i;
+            key = dubins_key(sx, sy, so.nx[g], so.ny[g], so.ca[g], so.sa[g]);
+            if (optimize) key = s_ce[i] + key;  // rrtplanner.cpp:254
+            idx = so.node_id[g];
+          }
+          unsigned wantm = __ballot_sync(FULL_MASK, key < T || (key == T && idx < Tid));
+          while (wantm) {
+            const int src = __ffs(wantm) - 1;
+            wantm &= wantm - 1;
+            const float nk = __shfl_sync(FULL_MASK, key, src);
+            const int nid = __shfl_sync(FULL_MASK, idx, src);
+            if (!(nk < T || (nk == T && nid < Tid))) continue;  // T moved since the ballot
+            if (lane == 0) NN_STAT(5, 1);
+            // position = number of entries ordered before the new one; entries from there on move down one lane
+            const bool before = lk < nk || (lk == nk && lid < nid);
+            const int pos = __popc(__ballot_sync(FULL_MASK, before && lane < CLRRT_SORT_LIMIT));
+            const float uk = __shfl_up_sync(FULL_MASK, lk, 1);
+            const int uid = __shfl_up_sync(FULL_MASK, lid, 1);
+            if (lane < CLRRT_SORT_LIMIT) {
+              if (lane == pos) { lk = nk; lid = nid; }
+              else if (lane > pos) { lk = uk; lid = uid; }
+            }
+            T = __shfl_sync(FULL_MASK, lk, CLRRT_SORT_LIMIT - 1);
+            Tid = __shfl_sync(FULL_MASK, lid, CLRRT_SORT_LIMIT - 1);
+          }
+        }
+        __syncwarp();
       }
-      __syncwarp();
-    }
     }
   }
   if (!live) return;
