@@ -74,6 +74,38 @@ def test_sequential_windows_equal_the_oracle_loop(clrrt, planner, seed, moving):
     assert st1.windows + st2.windows < 400, "speculation should commit more than one sample per window on average"
 
 
+def test_long_query_with_equal_keys_equals_the_oracle_loop(clrrt, planner):
+    """1500 iterations of the C1 query from the root.  With the optimise key the sums costE + length of the nodes along the
+    straight line from the root coincide for one sample in ten: the three routes for equal keys — they cannot change the
+    outcome (committed as speculated), the reference's own sort gives the same outcome (commit repeated), it does not (K = 1
+    host route) — must all occur here, and the tree must be the oracle's with std::sort's order of equal keys."""
+    car, goal = (0, 0, 0, 0, 0, 0), (50, 0, 0, 0)
+    obs = scene_c1_boxes()
+    orc = CpuPlanner("oracle")
+    orc.set_tie_mode(1)
+    orc.set_obstacles(obs)
+    orc.srand(1)
+    orc.tree_init(car, goal, 5.0)
+    planner.set_query(car, goal, 5.0)
+    planner.set_obstacles(obs)
+    planner.tree_reset_records(orc.tree_export())
+    c0 = orc.counters()
+    s, h, _ = orc.draw_samples(1500)
+    orc.expand_with(s, h)
+    st = planner.expand_sequential(s, h, window=0)
+    a, b = planner.tree_download_records(), orc.tree_export()
+    assert len(a) == len(b) == st.tree_size
+    assert np.array_equal(a[:, DISC_NODE], b[:, DISC_NODE])
+    assert rel_err(a, b).max() == 0.0
+    c1, gc = orc.counters(), planner.counters()
+    keys = ["fail_collision", "fail_acclimit", "fail_iterlimit", "sim_count"]
+    assert [gc[k] for k in keys] == [int(c1[k] - c0[k]) for k in keys]
+    print(f"1500 iterations: {st.windows} windows, {st.tie_checks_same} equal-key samples with the same outcome under the "
+          f"reference's sort, {st.exact_fallbacks} through the K = 1 route")
+    assert st.tie_checks_same > 0 and st.exact_fallbacks > 0
+    assert st.windows < 500
+
+
 def test_sequential_stops_at_a_full_tree(clrrt):
     pl = clrrt.Planner(device=0, tree_capacity=40, max_round=64)
     pl.set_query((0, 0, 0, 0, 0, 0), (50, 0, 0, 0), 5.0)
