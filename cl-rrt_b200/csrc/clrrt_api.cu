@@ -829,24 +829,27 @@ static int nearest_reference_ties(clrrt_ctx* ctx, const double* d_samples, const
 // nearest_reference_ties) and reports whether the OUTCOME is the same: the same candidates in the same order up to and
 // including the winner — or, when no candidate succeeded, the same set of candidates.  Then the window's rollouts stand
 // and only the commit is repeated; otherwise the K = 1 path runs the sample with the reference's list.
-static int window_tie_same_outcome(clrrt_ctx* ctx, const double* d_s, const uint8_t* d_h, bool* same) {
+static int window_tie_same_outcome(clrrt_ctx* ctx, const double* d_s, const uint8_t* d_h, int j, bool* same) {
   cudaStream_t st = ctx->stream;
   const int n = ctx->n_tree;
   *same = false;
   int32_t cand[CLRRT_SORT_LIMIT], cnt = 0;
   uint32_t word = 0;
   TieArgs t;
-  t.tree = ctx->tree; t.n_nodes = n; t.sample_xy = d_s; t.heuristic = d_h; t.feas_len = ctx->dprm.feas_len;
-  t.cand = ctx->d_cand; t.key = ctx->d_key; t.count = ctx->d_count; t.all_key = ctx->d_all_key; t.all_feas = ctx->d_all_feas; t.flag = ctx->d_ints + 6;
+  // (sample j of the window: its list was made against the tree at the start of the window; the nodes appended since are
+  // known not to come before its winner — seq_commit_kernel's conflict test — and the sort below runs over all of them)
+  t.tree = ctx->tree; t.n_nodes = n; t.sample_xy = d_s + 2 * (size_t)j; t.heuristic = d_h + j; t.feas_len = ctx->dprm.feas_len;
+  t.cand = ctx->d_cand + (size_t)j * CLRRT_SORT_LIMIT; t.key = ctx->d_key + (size_t)j * CLRRT_SORT_LIMIT; t.count = ctx->d_count + j;
+  t.all_key = ctx->d_all_key; t.all_feas = ctx->d_all_feas; t.flag = ctx->d_ints + 6;
   tie_check_kernel<<<(n + 127) / 128, 128, 0, st>>>(t);
   CK(cudaGetLastError());
   std::vector<float> key((size_t)n);
   std::vector<uint8_t> feas((size_t)n);
   CK(cudaMemcpyAsync(key.data(), ctx->d_all_key, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(feas.data(), ctx->d_all_feas, (size_t)n, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(cand, ctx->d_cand, sizeof cand, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(&cnt, ctx->d_count, sizeof cnt, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(&word, ctx->d_done, sizeof word, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(cand, ctx->d_cand + (size_t)j * CLRRT_SORT_LIMIT, sizeof cand, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&cnt, ctx->d_count + j, sizeof cnt, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&word, ctx->d_done + j, sizeof word, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   ctx->tie_sorts++;
   std::vector<std::pair<int, float>> dVector;
@@ -1301,7 +1304,7 @@ int clrrt_expand_sequential(clrrt_ctx* ctx, const double* sample_xy, const uint8
       }
       SeqCommitArgs c;
       c.tree = ctx->tree; c.stage = ctx->stage; c.n_tree = ctx->n_tree; c.capacity = ctx->cap; c.w = w; c.n_ranks = CLRRT_SORT_LIMIT;
-      c.skip_tie_first = 0;
+      c.j0 = 0; c.n_new0 = 0; c.skip_tie_first = 0;
       c.sample_xy = d_s; c.heuristic = d_h; c.key = ctx->d_key; c.count = ctx->d_count; c.sample_word = ctx->d_done;
       c.valid = ctx->d_valid; c.slot = ctx->d_slot; c.res_code = ctx->d_res_code; c.res_steps = ctx->d_res_steps; c.tie_flag = d_tie;
       c.feas_len = ctx->dprm.feas_len; c.counters = ctx->d_counters; c.out = ctx->d_ints + 8;
@@ -1316,35 +1319,38 @@ int clrrt_expand_sequential(clrrt_ctx* ctx, const double* sample_xy, const uint8
         cudaEventElapsedTime(&c2, ctx->ev[5], ctx->ev[2]); cudaEventElapsedTime(&d, ctx->ev[2], ctx->ev[4]);
         acc.ms_search += a; acc.ms_prepare += b; acc.ms_rollout += c2; acc.ms_commit += d;
       }
-      if (ctx->h_ints[10] == 1 && ctx->h_ints[8] == 0) {
-        // sample 0's outcome may hang on the order of equal keys: if the reference's own sort gives the same outcome, the
-        // window's rollouts stand and the commit is repeated with that check waived for sample 0
+      const int n_tree0 = ctx->n_tree;
+      int done = ctx->h_ints[8], n_new = ctx->h_ints[9], stop = ctx->h_ints[10];
+      ctx->n_tree = n_tree0 + n_new;
+      while (stop == 1) {
+        // sample `done` of the window: its outcome may hang on the order of equal keys.  If the reference's own sort gives
+        // the same outcome, the window's rollouts stand and the commit resumes there with that check waived.
         bool same = false;
-        if ((rc = window_tie_same_outcome(ctx, d_s, d_h, &same))) return rc;
-        if (same) {
-          CK(cudaMemsetAsync(ctx->d_ints + 8, 0, 3 * sizeof(int32_t), st));
-          c.skip_tie_first = 1;
-          seq_commit_kernel<<<1, SEQ_THREADS, 0, st>>>(c);
-          CK(cudaGetLastError());
-          CK(cudaMemcpyAsync(ctx->h_ints + 8, ctx->d_ints + 8, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-          CK(cudaStreamSynchronize(st));
-          acc.tie_checks_same++;
-        }
+        if ((rc = window_tie_same_outcome(ctx, d_s, d_h, done, &same))) return rc;
+        if (!same) break;
+        CK(cudaMemsetAsync(ctx->d_ints + 8, 0, 3 * sizeof(int32_t), st));
+        c.j0 = done; c.n_new0 = n_new; c.skip_tie_first = 1;
+        seq_commit_kernel<<<1, SEQ_THREADS, 0, st>>>(c);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ctx->h_ints + 8, ctx->d_ints + 8, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        done += ctx->h_ints[8]; n_new = ctx->h_ints[9]; stop = ctx->h_ints[10];
+        ctx->n_tree = n_tree0 + n_new;
+        acc.tie_checks_same++;
       }
-      const int committed = ctx->h_ints[8], appended = ctx->h_ints[9], stop = ctx->h_ints[10];
-      ctx->n_tree += appended;
-      acc.windows++; acc.nodes_added += appended; acc.speculated += w;
-      pos += committed;
+      acc.windows++; acc.nodes_added += n_new; acc.speculated += w;
+      pos += done;
       if (stop == 3) { ctx->err = "tree capacity exceeded"; rc_out = CLRRT_ERR_CAPACITY; pos = n; break; }
-      if (stop == 1 && committed == 0) {
-        // the first sample's own candidate list holds equal keys: the K = 1 path repeats the reference's std::sort
+      if (stop == 1) {
+        // the reference's order of equal keys gives this sample another outcome: the K = 1 path runs it with the reference's list
         clrrt_round_stats st1;
-        rc = clrrt_expand_round_dev(ctx, d_s, d_h, 1, &st1);
+        rc = clrrt_expand_round_dev(ctx, d_s + 2 * (size_t)done, d_h + done, 1, &st1);
         if (rc == CLRRT_ERR_CAPACITY) { rc_out = rc; pos = n; break; }
         if (rc) return rc;
         acc.exact_fallbacks++; acc.nodes_added += st1.nodes_added;
         pos += 1;
       }
+      const int committed = done;
       // window size: follow the length of the committed runs (a conflict wastes the rest of the window)
       if (window == 0) w_next = std::max(4, std::min(wmax, 2 * std::max(committed, 1) + 2));
     }

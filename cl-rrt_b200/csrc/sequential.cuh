@@ -71,8 +71,9 @@ __global__ void __launch_bounds__(128) tie_window_kernel(const TieWindowArgs a) 
 
 struct SeqCommitArgs {
   NodeSoA tree, stage;
-  int32_t n_tree, capacity, w, n_ranks;
-  int32_t skip_tie_first;      // 1: the host has checked sample 0's equal keys against the reference's order (same outcome)
+  int32_t n_tree, capacity, w, n_ranks;   // n_tree: size of the tree the window was speculated against
+  int32_t j0, n_new0;          // resume: first sample to commit, nodes the window has appended so far (0, 0 at first)
+  int32_t skip_tie_first;      // 1: the host has checked sample j0's equal keys against the reference's order (same outcome)
   const double* sample_xy;
   const uint8_t* heuristic;
   const float* key;            // [w][10]
@@ -106,27 +107,16 @@ __global__ void __launch_bounds__(SEQ_THREADS) seq_commit_kernel(const SeqCommit
   __shared__ int s_new;                       // nodes appended so far
   __shared__ unsigned long long s_cnt[5];
   const int tid = threadIdx.x;
-  if (tid == 0) { s_conflict = 0; s_new = 0; }
+  if (tid == 0) { s_conflict = 0; s_new = a.n_new0; }
   if (tid < 5) s_cnt[tid] = 0;
   __syncthreads();
   int committed = 0, stop = 0;
-  for (int j = 0; j < a.w; j++) {
+  for (int j = a.j0; j < a.w; j++) {
     const int n_new = s_new;
     // ---- does the speculation of sample j stand? ---------------------------------------------------------------------
     const int cnt = a.count[j];
     const int sb = __ffs(a.sample_word[j] >> 16) - 1;
     const bool won = sb >= 0 && sb < cnt;
-    // Equal keys: the reference's order is std::sort's (host path, K = 1).  The order can only change the outcome when it
-    // involves the WINNER (another feasible node with the winner's key may be tried first and succeed too) or, when no
-    // candidate succeeded, the last place of a full list (a node outside it with the same key may have taken that place
-    // and succeed).  Equal keys among candidates that fail anyway — tried in either order, counted either way — and
-    // among candidates after the winner, which are never tried (rrtplanner.cpp:150-160), leave the tree and the counters
-    // as they are.
-    {
-      const int tb = a.tie_flag[j];
-      const bool matters = (tb & SEQ_TIE_NAN) || (won ? ((tb >> sb) & 1) : (cnt == CLRRT_SORT_LIMIT && (tb & SEQ_TIE_OUTSIDE)));
-      if (matters && !(j == 0 && a.skip_tie_first)) { stop = 1; break; }
-    }
     if (j > 0 && n_new > 0) {
       float T;  // a feasible new node with key <= T would have been tried before the speculative outcome was reached
       if (won) T = a.key[(size_t)j * CLRRT_SORT_LIMIT + sb];
@@ -144,6 +134,17 @@ __global__ void __launch_bounds__(SEQ_THREADS) seq_commit_kernel(const SeqCommit
       }
       __syncthreads();
       if (s_conflict) { stop = 2; break; }
+    }
+    // Equal keys: the reference's order is std::sort's (host path, K = 1).  The order can only change the outcome when it
+    // involves the WINNER (another feasible node with the winner's key may be tried first and succeed too) or, when no
+    // candidate succeeded, the last place of a full list (a node outside it with the same key may have taken that place
+    // and succeed).  Equal keys among candidates that fail anyway — tried in either order, counted either way — and
+    // among candidates after the winner, which are never tried (rrtplanner.cpp:150-160), leave the tree and the counters
+    // as they are.
+    {
+      const int tb = a.tie_flag[j];
+      const bool matters = (tb & SEQ_TIE_NAN) || (won ? ((tb >> sb) & 1) : (cnt == CLRRT_SORT_LIMIT && (tb & SEQ_TIE_OUTSIDE)));
+      if (matters && !(j == a.j0 && a.skip_tie_first)) { stop = 1; break; }
     }
     // ---- commit: MyRRT::addNode for the winner and its goal-biased child (rrtplanner.cpp:156-158, :169-172) ------------
     const bool vm = a.valid[j] != 0, vg = a.valid[a.w + j] != 0;
