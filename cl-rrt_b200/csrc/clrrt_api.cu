@@ -255,12 +255,18 @@ template <typename R, bool ROUND> int launch_rollout_t(clrrt_ctx* ctx, const Rol
   return CLRRT_OK;
 }
 
-int launch_rollout(clrrt_ctx* ctx, const RolloutJob& job, int n_items_hint) {
+int launch_rollout(clrrt_ctx* ctx, const RolloutJob& job_in, int n_items_hint) {
+  RolloutJob job = job_in;
   const bool round = job.sample_word != nullptr;
   int per_sm = round ? ctx->blocks_per_sm_main : ctx->blocks_per_sm_gb;
   if (ctx->blocks_override > 0) per_sm = std::min(per_sm, ctx->blocks_override);
-  const int lanes_per_block = ROLLOUT_THREADS;
   int blocks = ctx->num_sms * per_sm;  // persistent grid: a multiple of the SM count
+  // Small launches (a sequential window, a batch of a few thousand rollouts) are latency-bound: a rollout alone in its warp
+  // takes 1.7 us per step, one of 32 diverging lanes several times that.  So the items are spread over ALL the warps of the
+  // persistent grid, `take_cap` lanes per warp at a time, instead of filling the first warps to the brim.
+  const int warps_per_block = ROLLOUT_THREADS / 32, warps = blocks * warps_per_block;
+  job.take_cap = std::max(1, std::min(32, (n_items_hint + warps - 1) / warps));
+  const int lanes_per_block = job.take_cap * warps_per_block;
   const int needed = (n_items_hint + lanes_per_block - 1) / lanes_per_block;
   if (needed < blocks) blocks = std::max(1, needed);
   if (round) return ctx->prm.fp32 ? launch_rollout_t<float, true>(ctx, job, blocks) : launch_rollout_t<double, true>(ctx, job, blocks);
