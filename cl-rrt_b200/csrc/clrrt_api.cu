@@ -106,6 +106,7 @@ struct clrrt_ctx {
   cudaEvent_t ev[7]{};
   int num_sms = 0, blocks_per_sm_main = 1, blocks_per_sm_gb = 1;
   size_t smem_bytes = 0;
+  bool nn_sorted_last = false;  // the last search sorted the samples (nn.sample_id holds their spatial order)
   int refill_min = 4;  // idle lanes a warp accumulates before fetching work (C3 at 8 warps/SM: 4: 3.99, 8: 4.02, 12: 4.06, 16: 4.18 ms)
   int blocks_override = 0;
   bool defer_append = false;
@@ -887,6 +888,7 @@ static int nearest_dev(clrrt_ctx* ctx, const double* d_samples, const uint8_t* d
                        float* d_key, int32_t* d_count, bool window = false) {
   const bool sorted = ctx->n_tree > 0 && (ctx->nn_mode == 1 || (ctx->nn_mode == 0 && (double)K * (double)ctx->n_tree >= NN_SORT_MIN_PAIRS));
   const bool ref_ties = K == 1 && ctx->tie_mode == 1 && !window;  // windows flag ties themselves (tie_window_kernel)
+  ctx->nn_sorted_last = sorted;
   if (ref_ties && !d_key) d_key = ctx->d_key;
   if (!sorted) {
     NearestArgs a;
@@ -1162,7 +1164,8 @@ static int round_core(clrrt_ctx* ctx, const double* d_sample_xy, const uint8_t* 
   ref_end_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(K, CLRRT_SORT_LIMIT, ctx->d_cand, CLRRT_SORT_LIMIT, ctx->d_count, d_sample_xy,
                                                        n_pairs, ctx->tree, ctx->d_ref_end, ctx->d_bucket, ctx->d_hist);
   order_scan_kernel<<<1, 1024, 0, st>>>(ctx->d_hist, CLRRT_SORT_LIMIT * ORDER_BUCKETS, ctx->d_ints + 2);
-  order_scatter_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(K, CLRRT_SORT_LIMIT, ctx->d_count, ctx->d_bucket, ctx->d_hist, ctx->d_order);
+  order_scatter_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(K, CLRRT_SORT_LIMIT, ctx->d_count, ctx->d_bucket, ctx->d_hist, ctx->d_order,
+                                                             ctx->nn_sorted_last ? ctx->nn.sample_id : nullptr);
   CK(cudaGetLastError());
   RolloutJob job;
   memset(&job, 0, sizeof job);
