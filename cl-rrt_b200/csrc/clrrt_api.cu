@@ -107,7 +107,10 @@ struct clrrt_ctx {
   int num_sms = 0, blocks_per_sm_main = 1, blocks_per_sm_gb = 1;
   size_t smem_bytes = 0;
   bool nn_sorted_last = false;  // the last search sorted the samples (nn.sample_id holds their spatial order)
-  int refill_min = 4;  // idle lanes a warp accumulates before fetching work (C3 at 8 warps/SM: 4: 3.99, 8: 4.02, 12: 4.06, 16: 4.18 ms)
+  // idle lanes a warp accumulates before fetching work.  With the launch order following the samples' positions a larger
+  // batch keeps the lanes of a warp together (C3 kernel: 1: 4.22, 2: 4.01, 4: 3.77, 8: 3.60, 12: 3.61, 16: 3.67, 24: 3.74 ms;
+  // with the round-1 order, unrelated neighbours, 4 was best)
+  int refill_min = 8;
   int blocks_override = 0;
   bool defer_append = false;
   int last_records = 0;
@@ -917,6 +920,8 @@ static int nearest_dev(clrrt_ctx* ctx, const double* d_samples, const uint8_t* d
   s.v0 = -8.0f;
   const float vbin_w = 16.0f / (float)(1 << s.nl_log2);
   s.inv_vbin = 1.0f / vbin_w;
+  s.inv_sbin = (float)((NN_BINS >> NN_SAMPLE_LAT_LOG2) / (dgoal + 40.0));
+  s.inv_svbin = (float)(1 << NN_SAMPLE_LAT_LOG2) / 16.0f;
   const int n_el = ctx->n_tree + K, n_tiles = (ctx->n_tree + NEAREST_TILE - 1) / NEAREST_TILE;
   CK(cudaMemsetAsync(s.hist, 0, (NN_HIST_INTS + 4) * sizeof(int32_t), st));
   nn_bin_kernel<<<(n_el + 255) / 256, 256, 0, st>>>(s);

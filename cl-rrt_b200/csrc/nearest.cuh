@@ -24,6 +24,9 @@
 // axis, NN_FCLS classes of 22.5 degrees), so that a tile of a large tree holds one or a few classes: that is what makes
 // the feasibility bound of a tile (nn_tile_kernel) effective.  Node bin = spatial bin * NN_FCLS + class.
 #define NN_FCLS 16
+#ifndef NN_SAMPLE_LAT_LOG2
+#define NN_SAMPLE_LAT_LOG2 4
+#endif
 #define NN_NODE_BINS (NN_BINS * NN_FCLS)
 #define NN_HIST_INTS (NN_NODE_BINS + 2 * NN_BINS)   // node bins; samples with the explore key; samples with the optimise key
 __constant__ float2 c_nn_fdir[NN_FCLS] = {   // centre direction of class c: angle -pi + (c + 0.5) 2 pi / 16
@@ -90,6 +93,7 @@ struct NNSortArgs {
   const uint8_t* heuristic;
   float cb, sb, u0, inv_bin;   // axis: slab = (u - u0) * inv_bin, NN_BINS >> nl_log2 slabs
   float v0, inv_vbin;          // lateral coordinate v = -x sb + y cb: 1 << nl_log2 bins from v0
+  float inv_sbin, inv_svbin;   // the same for the SAMPLE bins: NN_BINS >> NN_SAMPLE_LAT_LOG2 slabs x (1 << NN_SAMPLE_LAT_LOG2) lateral bins
   int32_t nl_log2;             // bin = slab << nl_log2 | lateral bin (0: axis only)
   int32_t* bin;        // [n_nodes + K] bin of every element (nodes first)
   int32_t* hist;       // [NN_HIST_INTS]: nodes; samples with the explore key; samples with the optimise key (so that the 8
@@ -129,9 +133,18 @@ __global__ void __launch_bounds__(256) nn_bin_kernel(const NNSortArgs a) {
     }
     else { x = (float)a.sample_xy[2 * (i - a.n_nodes)]; y = (float)a.sample_xy[2 * (i - a.n_nodes) + 1]; }
     const float u = x * a.cb + y * a.sb, v = y * a.cb - x * a.sb;
-    int b = (nn_bin_of(u, a.u0, a.inv_bin, NN_BINS >> a.nl_log2) << a.nl_log2) | nn_bin_of(v, a.v0, a.inv_vbin, 1 << a.nl_log2);
-    if (i < a.n_nodes) b = b * NN_FCLS + cls;
-    else if (a.heuristic[i - a.n_nodes]) b += NN_BINS;
+    int b;
+    if (i < a.n_nodes) {
+      b = (nn_bin_of(u, a.u0, a.inv_bin, NN_BINS >> a.nl_log2) << a.nl_log2) | nn_bin_of(v, a.v0, a.inv_vbin, 1 << a.nl_log2);
+      b = b * NN_FCLS + cls;
+    } else {
+      // samples: always (axis slab, lateral bin) cells, whatever the layout of the node bins — neighbours in the sorted order
+      // are neighbours in the plane: the 8 samples of a search block want the same tiles, and the launch order of the
+      // rollouts (order_scatter_kernel) follows this order so that the lanes of a warp meet the same obstacles
+      b = (nn_bin_of(u, a.u0, a.inv_sbin, NN_BINS >> NN_SAMPLE_LAT_LOG2) << NN_SAMPLE_LAT_LOG2) |
+          nn_bin_of(v, a.v0, a.inv_svbin, 1 << NN_SAMPLE_LAT_LOG2);
+      if (a.heuristic[i - a.n_nodes]) b += NN_BINS;
+    }
     a.bin[i] = b;
     key = (i < a.n_nodes ? 0 : NN_NODE_BINS) + b;
   }

@@ -7,6 +7,7 @@ import bench
 prm = clrrt.default_params(); prm.fp32 = 1 if os.environ.get('CLRRT_FP32') else 0
 pl = clrrt.Planner(params=prm, device=0, tree_capacity=bench.TREE_SNAPSHOT + 2 * bench.K_ROUND + 1024, max_round=bench.K_ROUND)
 boxes, smp, heu = bench.build_workload(pl, clrrt, 0, 1)
+if os.environ.get('REFILL_MIN'): pl.set_tuning(refill_min=int(os.environ['REFILL_MIN']))
 n0 = pl.tree_size()
 tag = os.environ.get("CLRRT_LIB", "default")
 for K in (bench.K_ROUND, 4096):
