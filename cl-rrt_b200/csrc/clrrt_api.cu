@@ -942,8 +942,8 @@ static int nearest_dev(clrrt_ctx* ctx, const double* d_samples, const uint8_t* d
   a.so.sample_id = s.sample_id; a.so.cb = s.cb; a.so.sb = s.sb;
   a.so.bin_end = s.hist; a.so.lead_sum = s.lead_sum; a.so.ce_floor = s.hist + NN_HIST_INTS + 1; a.so.u0 = s.u0; a.so.inv_bin = s.inv_bin; a.so.v0 = s.v0; a.so.inv_vbin = s.inv_vbin;
   a.so.nl_log2 = s.nl_log2;
-  const int blocks = (K + NEAREST_WARPS - 1) / NEAREST_WARPS;
-  nearest_sorted_kernel<<<blocks, NEAREST_THREADS, 0, ctx->stream>>>(a);
+  const int blocks = (K + NN_SORTED_WARPS - 1) / NN_SORTED_WARPS;
+  nearest_sorted_kernel<<<blocks, NN_SORTED_WARPS * 32, 0, ctx->stream>>>(a);
   CK(cudaGetLastError());
   if (ref_ties) return nearest_reference_ties(ctx, d_samples, d_heur, d_cand, d_key, d_count);
   return CLRRT_OK;

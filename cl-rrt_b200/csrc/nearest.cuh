@@ -17,6 +17,9 @@
 #define NEAREST_WARPS 8   // samples per block (16 measured: 1.12 against 1.10 ms on C3)
 #endif
 #define NEAREST_THREADS (NEAREST_WARPS * 32)
+#ifndef NN_SORTED_WARPS
+#define NN_SORTED_WARPS 8   // samples per block of the sorted search (C3: 2 / 4 / 8 / 16 -> 0.64 / 0.62 / 0.57 / 0.61 ms)
+#endif
 #define NEAREST_TILE 256
 
 #define NN_BINS 1024  // spatial bins of the sort (axis slab x lateral bin; the axis is the goal bearing)
@@ -427,22 +430,22 @@ __device__ unsigned long long g_nn_stats[8];  // tile steps, tiles loaded, warp-
 #else
 #define NN_STAT(k, v)
 #endif
-__global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const NearestArgs a) {
+__global__ void __launch_bounds__(NN_SORTED_WARPS * 32) nearest_sorted_kernel(const NearestArgs a) {
   // a tile stages seven floats per node (position, reference end, reference direction, costE): all that the distance bound
   // and the feasibility pre-test read; the double fields of the few survivors come straight from the sorted arrays
   __shared__ float s_fx[NEAREST_TILE], s_fy[NEAREST_TILE], s_ce[NEAREST_TILE];
   __shared__ float s_frx[NEAREST_TILE], s_fry[NEAREST_TILE], s_fdx[NEAREST_TILE], s_fdy[NEAREST_TILE];
-  __shared__ uint16_t s_idx[NEAREST_WARPS][NEAREST_TILE];
-  __shared__ uint16_t s_idx2[NEAREST_WARPS][NEAREST_TILE];
+  __shared__ uint16_t s_idx[NN_SORTED_WARPS][NEAREST_TILE];
+  __shared__ uint16_t s_idx2[NN_SORTED_WARPS][NEAREST_TILE];
   __shared__ int s_start;
-  __shared__ float s_sp[NEAREST_WARPS][NN_FCLS];   // sample . f_c (+ rounding) for the feasibility bound of a tile
+  __shared__ float s_sp[NN_SORTED_WARPS][NN_FCLS];   // sample . f_c (+ rounding) for the feasibility bound of a tile
   __shared__ unsigned s_mask[3][2];   // per chunk of 32 tiles: wanted by any sample / axis-open for any sample (3 in rotation)
   const NearestSorted& so = a.so;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   // position in the sorted sample order; last blocks first: the optimise-key samples are sorted after the explore-key ones
   // and take about three times as long each, so they are started first and the short blocks fill in behind them
-  const int js = (gridDim.x - 1 - blockIdx.x) * NEAREST_WARPS + warp;
+  const int js = (gridDim.x - 1 - blockIdx.x) * NN_SORTED_WARPS + warp;
   const bool live = js < a.K;
   const int j = live ? so.sample_id[js] : 0;
   double sx = 0, sy = 0;
@@ -573,11 +576,11 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_sorted_kernel(const N
       const int base = t * NEAREST_TILE;
       const int n = min(NEAREST_TILE, so.n_nodes - base);
       if (threadIdx.x == 0) NN_STAT(1, 1);
-      if ((int)threadIdx.x < n) {
-        const int g = base + threadIdx.x;
-        s_fx[threadIdx.x] = so.fx[g]; s_fy[threadIdx.x] = so.fy[g]; s_ce[threadIdx.x] = so.ce[g];
-        s_frx[threadIdx.x] = so.frx[g]; s_fry[threadIdx.x] = so.fry[g];
-        s_fdx[threadIdx.x] = so.fdx[g]; s_fdy[threadIdx.x] = so.fdy[g];
+      for (int q = threadIdx.x; q < n; q += NN_SORTED_WARPS * 32) {
+        const int g = base + q;
+        s_fx[q] = so.fx[g]; s_fy[q] = so.fy[g]; s_ce[q] = so.ce[g];
+        s_frx[q] = so.frx[g]; s_fry[q] = so.fry[g];
+        s_fdx[q] = so.fdx[g]; s_fdy[q] = so.fdy[g];
       }
       __syncthreads();
       if (want) {
