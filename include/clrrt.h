@@ -278,7 +278,7 @@ int clrrt_append_records(clrrt_ctx* ctx, const void* d_records, const int32_t* c
 
 int clrrt_get_device(const clrrt_ctx* ctx);
 /* Launch tuning of the rollout kernel: refill_min = idle lanes a warp accumulates before it fetches new work
- * (default 4; 1 = refill immediately); blocks_per_sm = resident blocks of the persistent grid (0 = occupancy maximum). */
+ * (default 8; 1 = refill immediately); blocks_per_sm = resident blocks of the persistent grid (0 = occupancy maximum). */
 int clrrt_set_tuning(clrrt_ctx* ctx, int refill_min, int blocks_per_sm);
 /* Order of EQUAL keys in the candidate list.  The reference sorts (node id, key) pairs with std::sort on the key alone
  * (rrt/src/rrtplanner.cpp:233, :256), so equal keys end up in whatever order libstdc++'s introsort leaves them.
